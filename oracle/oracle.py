@@ -1,0 +1,327 @@
+"""CPU oracle for the pileup -> consensus -> SNP-matrix -> distance hot path.
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and the cpu_baseline /
+``--impl reference`` legs of bench.py; the product package never imports it.
+
+The arithmetic lives in ``snp_oracle.c`` (compiled here with gcc into ``oracle/_build/liboracle.so``);
+this module adds the file-level behaviour of the reference's four subcommands as small pure-Python
+functions, each citing the reference lines it restates (paths relative to the upstream repository).
+
+Third-party pieces the reference leans on and that are NOT in its tree (named + restated here):
+  * PyVCF3 ~=1.0.3 (setup.py:25) -- ``vcf.Reader`` as used at utils.py:1127: only CHROM and POS are consumed.
+    Restated in :func:`vcf_sites`; pinned by the bundled snplist*.txt golden files (lambda/agona/listeria).
+  * Biopython (setup.py:28) -- ``SeqIO.write(..., "fasta")`` as called at call_consensus.py:189-192.
+    Restated in :func:`fasta_text`; pinned by every bundled consensus*.fasta / snpma*.fasta.
+Parity status: PINNED (tests/test_oracle_golden.py, tests/test_oracle_vs_reference.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import itertools
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "snp_oracle.c")
+_BUILD = os.path.join(_HERE, "_build")
+_SO = os.path.join(_BUILD, "liboracle.so")
+
+FAIL_RAWDPTH, FAIL_VARFREQ, FAIL_DEPTH, FAIL_STRDPTH, FAIL_STRBIAS, FAIL_REGION = 1, 2, 4, 8, 16, 32
+E_OK, E_VALUE, E_INDEX, E_UNPACK, E_DOMAIN = 0, 1, 2, 3, 4
+
+
+class OracleError(Exception):
+    """The reference would raise on this input (status = ORACLE_E_*, line = 0-based line index)."""
+
+    def __init__(self, status, line):
+        super().__init__("oracle: reference raises (status %d) at line %d" % (status, line))
+        self.status = status
+        self.line = line
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("min_base_qual", ctypes.c_int), ("min_cons_freq", ctypes.c_double),
+                ("min_cons_depth", ctypes.c_int), ("min_cons_strand_depth", ctypes.c_int),
+                ("min_cons_strand_bias", ctypes.c_double)]
+
+
+def make_params(min_base_qual=0, min_cons_freq=0.6, min_cons_depth=1, min_cons_strand_depth=0,
+                min_cons_strand_bias=0.0):
+    return Params(int(min_base_qual), float(min_cons_freq), int(min_cons_depth), int(min_cons_strand_depth),
+                  float(min_cons_strand_bias))
+
+
+def build(force=False):
+    """Compile snp_oracle.c (gcc -O2).  Returns the path of the shared object."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        os.makedirs(_BUILD, exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", _SO, _SRC])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        u8p, i32p, i64p, u32p, u64p = (ctypes.POINTER(t) for t in
+                                       (ctypes.c_uint8, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32,
+                                        ctypes.c_uint64))
+        L.oracle_strip.restype = ctypes.c_size_t
+        L.oracle_strip.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+        L.oracle_line_report.restype = None
+        L.oracle_line_report.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(Params), i32p]
+        L.oracle_pileup_consensus.restype = ctypes.c_int
+        L.oracle_pileup_consensus.argtypes = [
+            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, i32p, ctypes.c_int,
+            i32p, i64p, ctypes.c_size_t, i32p, i64p, ctypes.c_size_t, ctypes.POINTER(Params), ctypes.c_int,
+            u8p, u8p, u8p, i64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+        L.oracle_merge_sites.restype = ctypes.c_size_t
+        L.oracle_merge_sites.argtypes = [u64p, u32p, ctypes.c_size_t, u64p, u32p, u32p]
+        L.oracle_distance.restype = None
+        L.oracle_distance.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p]
+        L.oracle_distance_rows.restype = None
+        L.oracle_distance_rows.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p, ctypes.c_size_t,
+                                           ctypes.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+# ----------------------------------------------------------------------------- per-line (pileup.py)
+def strip_bases(bases: bytes) -> bytes:
+    """pileup.py:276-325 Record._strip_unwanted_base_patterns."""
+    out = ctypes.create_string_buffer(len(bases) + 1)
+    n = lib().oracle_strip(bases, len(bases), out)
+    return out.raw[:n]
+
+
+def line_report(line: bytes, params: Params) -> dict:
+    """pileup.py:209-274 + 492-590 on one line: tallies, ranking, consensus byte and fail mask."""
+    out = np.zeros(13 + 4 * 128, dtype=np.int32)
+    lib().oracle_line_report(line, len(line), ctypes.byref(params), _ptr(out, ctypes.c_int32))
+    tot, fwd, rev, common = (out[13 + k * 128: 13 + (k + 1) * 128] for k in range(4))
+    n_common = int(out[10])
+    as_counter = lambda v: {chr(c): int(v[c]) for c in range(128) if v[c]}
+    return {
+        "status": int(out[0]), "ntok": int(out[1]),
+        "pos": (int(out[3]) << 32) | (int(out[2]) & 0xffffffff),
+        "raw_depth": (int(out[5]) << 32) | (int(out[4]) & 0xffffffff),
+        "ref": chr(out[6]) if out[6] else "", "good_depth": int(out[7]), "fwd_good_depth": int(out[8]),
+        "rev_good_depth": int(out[9]),
+        "most_common": [chr(c) for c in common[:n_common]] if n_common else None,
+        "total": as_counter(tot), "fwd": as_counter(fwd), "rev": as_counter(rev),
+        "cons": chr(out[11]), "fail": int(out[12]),
+    }
+
+
+def fail_names(mask: int, params: Params):
+    """Filter names in the order pileup.py:556-584 / call_consensus.py:165-168 appends them (None if none)."""
+    names = []
+    if mask & FAIL_RAWDPTH:
+        names.append("RawDpth")
+    if mask & FAIL_VARFREQ:
+        names.append("VarFreq" + str(int(100 * params.min_cons_freq)))
+    if mask & FAIL_DEPTH:
+        names.append("Depth" + str(params.min_cons_depth))
+    if mask & FAIL_STRDPTH:
+        names.append("StrDpth" + str(params.min_cons_strand_depth))
+    if mask & FAIL_STRBIAS:
+        names.append("StrBias" + str(int(100 * params.min_cons_strand_bias)))
+    if mask & FAIL_REGION:
+        names.append("Region")
+    return names or None
+
+
+# ----------------------------------------------------------------------------- per-sample driver
+def contig_table(names):
+    """names: list of bytes -> (concatenated bytes, int32 offsets) as the C entry point wants them."""
+    blob = b"".join(names)
+    off = np.zeros(len(names) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(n) for n in names])
+    return blob, off
+
+
+def pileup_consensus(text, snp_list, excluded, params: Params, parse_all=False, want_lines=False):
+    """call_consensus.py:142-188 for one sample.
+
+    text      bytes / uint8 ndarray holding the pileup file
+    snp_list  [(chrom: str, pos: int)] in snplist.txt order (duplicates allowed)
+    excluded  iterable of (chrom, pos)
+    Returns the consensus row (bytes, len(snp_list)); with want_lines also (cells, fails, positions) of every
+    parsed line in file order.  Raises OracleError where the reference raises.
+    """
+    buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text)
+    excluded = list(excluded)
+    names = sorted({c for c, _ in snp_list} | {c for c, _ in excluded})
+    idx = {c: i for i, c in enumerate(names)}
+    blob, off = contig_table([n.encode() for n in names])
+    sc = np.array([idx[c] for c, _ in snp_list], dtype=np.int32)
+    sp = np.array([p for _, p in snp_list], dtype=np.int64)
+    ec = np.array([idx[c] for c, _ in excluded], dtype=np.int32)
+    ep = np.array([p for _, p in excluded], dtype=np.int64)
+    row = np.zeros(max(len(snp_list), 1), dtype=np.uint8)
+    max_lines = 0
+    lc = lf = lp = None
+    if want_lines:
+        max_lines = int(np.count_nonzero(buf == 10) + np.count_nonzero(buf == 13) + 1)
+        lc = np.zeros(max_lines, dtype=np.uint8)
+        lf = np.zeros(max_lines, dtype=np.uint8)
+        lp = np.zeros(max_lines, dtype=np.int64)
+    n_parsed = ctypes.c_size_t(0)
+    err_line = ctypes.c_size_t(0)
+    u8, i32, i64 = ctypes.c_uint8, ctypes.c_int32, ctypes.c_int64
+    rc = lib().oracle_pileup_consensus(
+        buf.ctypes.data, buf.size, blob, _ptr(off, i32), len(names),
+        _ptr(sc, i32), _ptr(sp, i64), len(snp_list), _ptr(ec, i32), _ptr(ep, i64), len(excluded),
+        ctypes.byref(params), 1 if parse_all else 0, _ptr(row, u8),
+        _ptr(lc, u8) if want_lines else None, _ptr(lf, u8) if want_lines else None,
+        _ptr(lp, i64) if want_lines else None, max_lines, ctypes.byref(n_parsed), ctypes.byref(err_line))
+    if rc != 0:
+        raise OracleError(rc, err_line.value)
+    row_b = row[:len(snp_list)].tobytes()
+    if want_lines:
+        n = n_parsed.value
+        return row_b, (lc[:n], lf[:n], lp[:n])
+    return row_b
+
+
+# ----------------------------------------------------------------------------- file formats
+_ROW_SPLIT = re.compile("\t| +")
+
+
+def vcf_sites(path):
+    """utils.py:1113-1132 convert_vcf_file_to_snp_set, with PyVCF3's Reader restated.
+
+    PyVCF3 1.0.3 ``vcf/parser.py``: the Reader strips every line and drops blank ones, consumes the leading
+    ``##`` meta lines and the ``#CHROM`` header line, then for each following line splits
+    ``line.rstrip()`` on ``'\\t| +'`` and takes ``CHROM = row[0]``, ``POS = int(row[1])``.
+    Returns the ordered list of (chrom, pos) with duplicates removed (a set in the reference).
+    """
+    seen = {}
+    with open(path, "r") as f:
+        lines = (ln.strip() for ln in f)
+        lines = [ln for ln in lines if ln]
+    i = 0
+    while i < len(lines) and lines[i].startswith("##"):
+        i += 1
+    if i >= len(lines):
+        raise ValueError("vcf: no header line")     # PyVCF: next() on the exhausted reader inside __init__
+    i += 1                                          # the first non-## line is the column header, whatever it is
+    for ln in lines[i:]:
+        row = _ROW_SPLIT.split(ln.rstrip())
+        if len(row) < 8:
+            raise IndexError("vcf: fewer than 8 columns")
+        seen[(row[0], int(row[1]))] = True
+    return list(seen)
+
+
+def read_snp_list(path):
+    """utils.py:1073-1088 read_snp_position_list."""
+    out = []
+    with open(path, "r") as f:
+        for line in f:
+            chrom, pos = line.split()[0:2]
+            out.append((chrom, int(pos)))
+    return out
+
+
+def merge_sites_text(sample_dirs, vcf_name="var.flt.vcf", max_snps=-1):
+    """merge_sites.py:69-131 + utils.py:1056-1070.  Returns (snplist text, filtered sample-dir text)."""
+    unsorted = [d for d in (ln.rstrip() for ln in sample_dirs) if d]
+    snp_dict, excluded_dirs = {}, set()
+    for d in sorted(unsorted):
+        vcf = os.path.join(d, vcf_name)
+        if not os.path.isfile(vcf) or os.path.getsize(vcf) == 0:
+            continue
+        name = os.path.basename(os.path.dirname(vcf))
+        sites = vcf_sites(vcf)
+        if max_snps >= 0 and len(sites) > max_snps:
+            excluded_dirs.add(d)
+            continue
+        for key in sites:
+            snp_dict.setdefault(key, []).append(name)
+    text = "".join("%s\t%d\t%d\t%s\n" % (k[0], k[1], len(v), "\t".join(v)) for k, v in sorted(snp_dict.items()))
+    filt = "".join("%s\n" % d for d in unsorted if d not in excluded_dirs)
+    return text, filt
+
+
+def merge_sites_keys(keys, sample_of):
+    """C restatement of the union on packed keys (tests the radix-sort/unique kernel)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    sample_of = np.ascontiguousarray(sample_of, dtype=np.uint32)
+    n = keys.size
+    uniq = np.zeros(max(n, 1), dtype=np.uint64)
+    cnt = np.zeros(max(n, 1), dtype=np.uint32)
+    samples = np.zeros(max(n, 1), dtype=np.uint32)
+    u = lib().oracle_merge_sites(_ptr(keys, ctypes.c_uint64), _ptr(sample_of, ctypes.c_uint32), n,
+                                 _ptr(uniq, ctypes.c_uint64), _ptr(cnt, ctypes.c_uint32),
+                                 _ptr(samples, ctypes.c_uint32))
+    return uniq[:u], cnt[:u], samples[:n]
+
+
+def fasta_text(seq_id: str, seq: str) -> str:
+    """Bio.SeqIO FastaWriter as called at call_consensus.py:189-192 (description ""): 60-column wrap."""
+    lines = [">%s\n" % seq_id]
+    for i in range(0, len(seq), 60):
+        lines.append(seq[i:i + 60] + "\n")
+    return "".join(lines)
+
+
+def read_fasta_matrix(path):
+    """distance.py:76-84."""
+    seqs = {}
+    cur = None
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                cur = line.lstrip(">")
+                seqs[cur] = ""
+            else:
+                seqs[cur] += line
+    return seqs
+
+
+def distance_matrix(rows):
+    """utils.py:1135-1165 over all pairs: rows = equal-length byte strings -> int32 [n, n]."""
+    n = len(rows)
+    s = len(rows[0]) if n else 0
+    m = np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(n, s).copy() if n and s else np.zeros((n, max(s, 1)), np.uint8)
+    d = np.zeros((n, n), dtype=np.int32)
+    if n:
+        lib().oracle_distance(_ptr(m, ctypes.c_uint8), n, s, _ptr(d, ctypes.c_int32))
+    return d
+
+
+def distance_texts(seqs):
+    """distance.py:90-115: (pairwise TSV text, matrix TSV text) from {id: sequence}."""
+    ids = sorted(seqs)
+    for a, b in itertools.combinations(ids, 2):
+        if len(seqs[b]) < len(seqs[a]):
+            raise IndexError("string index out of range")
+    # the reference walks range(len(seq1)) for each sorted pair (a, b): compare over len(a)
+    lens = [len(seqs[i]) for i in ids]
+    if len(set(lens)) <= 1:
+        d = distance_matrix([seqs[i].encode() for i in ids]) if ids else np.zeros((0, 0), np.int32)
+    else:
+        d = np.zeros((len(ids), len(ids)), np.int32)
+        for (i, a), (j, b) in itertools.combinations(enumerate(ids), 2):
+            la = len(seqs[a])
+            d[i, j] = d[j, i] = distance_matrix([seqs[a].encode(), seqs[b][:la].encode()])[0, 1]
+    pair = ["Seq1\tSeq2\tDistance\n"]
+    for i, a in enumerate(ids):
+        for j, b in enumerate(ids):
+            pair.append("%s\t%s\t%i\n" % (a, b, d[i, j]))
+    mat = ["\t%s\n" % "\t".join(ids)]
+    for i, a in enumerate(ids):
+        mat.append("%s\t%s\n" % (a, "\t".join(str(int(x)) for x in d[i])))
+    return "".join(pair), "".join(mat)
