@@ -1,0 +1,175 @@
+/*
+ * snpgpu.h -- C ABI of libsnpgpu.so: the B200 (sm_100a) implementation of the CFSAN SNP Pipeline's
+ * pileup -> consensus -> site-union -> SNP-matrix -> pairwise-distance hot path.
+ *
+ * The reference (CFSAN-Biostatistics/snp-pipeline) is pure Python with no FFI of its own; the surface it
+ * offers for this path is four subcommand functions that talk through files.  Each
+ * entry point below replaces the arithmetic of one reference function and is what a ctypes binding inside
+ * that function would call (INTEGRATION.md shows the stubs).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an SNPGPU_E_* code; snpgpu_last_error() gives the text.
+ *   - "_dev" pointers are CUDA device pointers in the context's device; everything else is host memory.
+ *   - work is enqueued on the context's stream (snpgpu_set_stream); calls that return results to host
+ *     memory synchronise that stream before returning, "_dev"/"_async" calls do not.
+ *   - one context per host thread / per GPU; a context is not thread-safe.
+ */
+#ifndef SNPGPU_H
+#define SNPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNPGPU_ABI_VERSION 1
+
+/* ---- status codes ----------------------------------------------------------------------------- */
+#define SNPGPU_OK            0
+#define SNPGPU_E_VALUE       1   /* the reference raises ValueError (malformed integer column)              */
+#define SNPGPU_E_INDEX       2   /* the reference raises IndexError (too few columns for pileup.Record)      */
+#define SNPGPU_E_UNPACK      3   /* the reference raises ValueError (fewer than 2 columns, filter mode)      */
+#define SNPGPU_E_DOMAIN      4   /* input outside the byte / int64 domain (non-ASCII byte, |int| >= 2^63,    */
+                                 /* reference-base column not exactly one byte)                              */
+#define SNPGPU_E_LONECR      5   /* a line ends in a lone CR (classic Mac).  Python's universal newlines end a   */
+                                 /* line there (pileup.py:417); the kernels split on LF only.  The host-buffer   */
+                                 /* entry point rewrites such CRs to LF in its device copy and runs again; users */
+                                 /* of the _dev entry point call snpgpu_normalize_newlines_dev and repeat         */
+#define SNPGPU_E_CUDA        16  /* a CUDA runtime call or kernel failed                                     */
+#define SNPGPU_E_ARG         17  /* bad argument (null pointer, misaligned device buffer, size overflow)     */
+#define SNPGPU_E_NOMEM       18  /* device or host allocation failed                                         */
+#define SNPGPU_E_LENGTH      19  /* distance: a later (sorted) sequence is shorter than an earlier one --    */
+                                 /* the reference raises IndexError at utils.py:1158                         */
+
+/* ---- fail-filter bits (pileup.py:556-584, call_consensus.py:165-168) ---------------------------- */
+#define SNPGPU_FAIL_RAWDPTH  1
+#define SNPGPU_FAIL_VARFREQ  2
+#define SNPGPU_FAIL_DEPTH    4
+#define SNPGPU_FAIL_STRDPTH  8
+#define SNPGPU_FAIL_STRBIAS 16
+#define SNPGPU_FAIL_REGION  32
+
+typedef struct snpgpu_ctx snpgpu_ctx;
+typedef struct snpgpu_sites snpgpu_sites;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int         snpgpu_abi_version(void);
+int         snpgpu_create(int device, snpgpu_ctx **out);
+void        snpgpu_destroy(snpgpu_ctx *ctx);
+const char *snpgpu_last_error(const snpgpu_ctx *ctx);
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = the context's own stream */
+int         snpgpu_set_stream(snpgpu_ctx *ctx, void *stream);
+int         snpgpu_sync(snpgpu_ctx *ctx);
+/* pinned host memory for the streaming entry points */
+int         snpgpu_host_alloc(snpgpu_ctx *ctx, size_t nbytes, void **out);
+int         snpgpu_host_free(snpgpu_ctx *ctx, void *p);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t    snpgpu_launch_count(const snpgpu_ctx *ctx);
+
+/* ---- consensus-caller parameters: ConsensusCaller.__init__ (pileup.py:433-471) + Reader's
+ *      min_base_quality (pileup.py:389-407) -------------------------------------------------------- */
+typedef struct {
+    int32_t min_base_qual;          /* call_consensus -q  (cfsan_snp_pipeline.py:397) */
+    int32_t min_cons_depth;         /* -D */
+    int32_t min_cons_strand_depth;  /* -d */
+    int32_t reserved;
+    double  min_cons_freq;          /* -c, compared in IEEE double like the reference (pileup.py:564) */
+    double  min_cons_strand_bias;   /* -b, pileup.py:580 */
+} snpgpu_params;
+
+/* ---- site table: snplist.txt entries (utils.py:1073-1088) plus the exclude VCF's positions
+ *      (call_consensus.py:117-125).  snp entries keep file order and may repeat. ------------------- */
+int  snpgpu_sites_create(snpgpu_ctx *ctx,
+                         const char *contig_names, const int32_t *name_off, int32_t n_contigs,
+                         const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp,
+                         const int32_t *exc_contig, const int64_t *exc_pos, size_t n_exc,
+                         snpgpu_sites **out);
+void snpgpu_sites_destroy(snpgpu_sites *sites);
+size_t snpgpu_sites_n_snp(const snpgpu_sites *sites);
+
+/* ---- K1: pileup text -> consensus cells.  Replaces pileup.Reader.__iter__ + Record + ConsensusCaller +
+ *      the loop body of call_consensus.py:161-188.
+ *   mode SNPGPU_MODE_SITES   only lines whose (chrom,pos) is in the site table are parsed (pileup.py:423-429)
+ *   mode SNPGPU_MODE_ALL     every line is parsed (--vcfAllPos, pileup.py:419-421); line_out, when given,
+ *                            receives one uint16 per line in file order: low byte = matrix cell, high byte =
+ *                            fail mask.
+ *   row_out[n_snp]           the consensus string in snplist order ('-' where nothing was called).
+ *   stats (nullable)         see snpgpu_pileup_stats.
+ * On SNPGPU_E_VALUE/INDEX/UNPACK/DOMAIN stats->error_offset is the byte offset of the first offending
+ * line in file order -- the line at which the reference's exception would surface. ----------------- */
+#define SNPGPU_MODE_SITES 0
+#define SNPGPU_MODE_ALL   1
+
+typedef struct {
+    uint64_t n_lines;        /* lines seen                                              */
+    uint64_t n_parsed;       /* lines that went through tally + consensus call          */
+    uint64_t n_general;      /* of those, lines that needed the general (non-fast) path */
+    uint64_t error_offset;   /* byte offset of the first raising line, or UINT64_MAX    */
+    int32_t  error_code;
+    int32_t  reserved;
+} snpgpu_pileup_stats;
+
+/* text in host memory (pinned or pageable); copies are streamed inside the call */
+int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes,
+                            const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                            uint8_t *row_out, uint16_t *line_out, size_t line_out_cap,
+                            snpgpu_pileup_stats *stats);
+
+/* text already in device memory (16-byte aligned).  row_out_dev: n_snp bytes.  line_out_dev: nullable,
+ * one uint16 per line in file order, capacity line_out_cap.  stats_dev: nullable device copy of
+ * snpgpu_pileup_stats (valid after the stream is synchronised).  Nothing is synchronised here. */
+int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes,
+                                const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                                uint8_t *row_out_dev, uint16_t *line_out_dev, size_t line_out_cap,
+                                snpgpu_pileup_stats *stats_dev);
+
+/* Rewrites every CR that is not followed by LF to LF, in place (byte offsets and line structure under
+ * universal newlines are unchanged).  Needed only after SNPGPU_E_LONECR. */
+int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes);
+
+/* ---- K2: union of variant sites.  Replaces the dict-of-lists loop of merge_sites.py:94-116 and the
+ *      sorted() of utils.py:1068.  keys[i] = (chrom_rank << 32) | pos with chrom_rank in chromosome
+ *      *string* order; sample_of[i] = index of the owning sample in sorted-sample-directory order, samples
+ *      concatenated in that order.  Outputs (caller-allocated, capacity n each): unique keys ascending,
+ *      per-key sample count, and sample indices grouped by key (input order kept inside a group). ------ */
+int snpgpu_merge_sites(snpgpu_ctx *ctx, const uint64_t *keys, const uint32_t *sample_of, size_t n,
+                       uint64_t *uniq_out, uint32_t *count_out, uint32_t *samples_out, size_t *n_uniq_out);
+int snpgpu_merge_sites_dev(snpgpu_ctx *ctx, const uint64_t *keys_dev, const uint32_t *sample_of_dev, size_t n,
+                           uint64_t *uniq_out_dev, uint32_t *count_out_dev, uint32_t *samples_out_dev,
+                           size_t *n_uniq_out /* host; synchronises */);
+
+/* ---- K4: all-pairs SNP distance.  Replaces utils.calculate_sequence_distance (utils.py:1135-1165) over
+ *      itertools.combinations (distance.py:93-96).  matrix: n_rows x row_stride bytes, row i holding
+ *      n_sites valid bytes; only columns where both bytes are in {A,C,G,T} (case-insensitive) count.
+ *      dist_out: n_rows x n_rows int32, symmetric, zero diagonal.
+ *      The stripe variant computes rows [row_begin,row_end) of the output only (multi-GPU sharding). ---- */
+int snpgpu_pairwise_distance(snpgpu_ctx *ctx, const uint8_t *matrix, size_t n_rows, size_t n_sites,
+                             size_t row_stride, int32_t *dist_out);
+int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
+                                 size_t row_stride, size_t row_begin, size_t row_end, int32_t *dist_out_dev);
+
+/* ---- synthetic pileup generator (bench / tests only; SURVEY.md section 8d's input spec).
+ *      Writes one sample's pileup text into text_dev (capacity cap bytes) and returns its length.  The text
+ *      depends only on (seed, sample, the arguments) so any sample can be regenerated on any rank. -------- */
+typedef struct {
+    uint64_t seed;
+    uint32_t sample;
+    uint32_t genome_len;       /* positions 1..genome_len on one contig                              */
+    uint32_t mean_depth;       /* ~Poisson-shaped, clipped to [0, 60]                                */
+    uint32_t n_pool_sites;     /* size of the global variant-site pool (same for every sample)       */
+    float    site_carry_prob;  /* probability that this sample carries a given pool site             */
+    float    reserved;
+} snpgpu_synth_spec;
+
+int snpgpu_synth_pileup_dev(snpgpu_ctx *ctx, const snpgpu_synth_spec *spec, const char *contig_name,
+                            void *text_dev, size_t cap, size_t *nbytes_out /* host; synchronises */);
+/* positions (1-based, ascending) of the pool sites this sample carries; returns how many */
+int snpgpu_synth_sample_sites(snpgpu_ctx *ctx, const snpgpu_synth_spec *spec, uint32_t *pos_out, size_t cap,
+                              size_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNPGPU_H */

@@ -1,0 +1,425 @@
+// api.cu -- the C ABI of libsnpgpu.so (include/snpgpu.h): contexts, the device-resident site table, and the
+// host-side sequencing of the kernels.  No kernels of its own.
+#include "internal.h"
+#include "sites_host.h"
+
+#include <algorithm>
+#include <new>
+#include <stdio.h>
+#include <string>
+#include <string.h>
+#include <vector>
+
+using namespace snpgpu;
+
+namespace {
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = (n + (n >> 3) + 4095) & ~(size_t)4095;       // a little slack so growth is rare
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct snpgpu_ctx {
+    int          device = 0;
+    int          n_sms = 148;
+    int          k1_blocks[2] = {1, 1};      // resident CTAs per SM of the pileup kernel, [has_qual]
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint64_t     launches = 0;
+    std::string  err;
+    DevBuf status, site_cells, stage, tile_nlines, tile_prefix, arena, stats;
+    DevBuf text, row, lines;                  // staging of the host-buffer entry points
+    DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
+    DevBuf k4_tmp, k4_mat, k4_dist;
+    DevBuf synth_tmp, synth_n;
+    size_t arena_want = 1 << 20;
+};
+
+struct snpgpu_sites {
+    snpgpu_ctx *ctx = nullptr;
+    size_t n_snp = 0, n_unique = 0;
+    int n_contigs = 0;
+    void *blob = nullptr;                     // one device allocation holding every array below
+    SiteTable table;                          // device pointers
+    int32_t *snp_unique = nullptr;            // device, n_snp: unique-site index of snplist entry k
+};
+
+static int fail(snpgpu_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? SNPGPU_E_NOMEM : SNPGPU_E_CUDA, #call, e_); \
+    } while (0)
+
+extern "C" {
+
+int snpgpu_abi_version(void) { return SNPGPU_ABI_VERSION; }
+
+int snpgpu_create(int device, snpgpu_ctx **out) {
+    if (!out) return SNPGPU_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return SNPGPU_E_CUDA;   // no CPU fallback: fail loudly
+    if (device < 0 || device >= n) return SNPGPU_E_ARG;
+    snpgpu_ctx *ctx = new (std::nothrow) snpgpu_ctx();
+    if (!ctx) return SNPGPU_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return SNPGPU_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SNPGPU_E_CUDA; }
+    ctx->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SNPGPU_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    ctx->k1_blocks[0] = std::max(1, k1_blocks_per_sm(false));
+    ctx->k1_blocks[1] = std::max(1, k1_blocks_per_sm(true));
+    if (cudaGetLastError() != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return SNPGPU_E_CUDA; }
+    *out = ctx;
+    return SNPGPU_OK;
+}
+
+void snpgpu_destroy(snpgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = {&ctx->status, &ctx->site_cells, &ctx->stage, &ctx->tile_nlines, &ctx->tile_prefix, &ctx->arena,
+                     &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
+                     &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
+                     &ctx->synth_tmp, &ctx->synth_n};
+    for (DevBuf *b : all) b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *snpgpu_last_error(const snpgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int snpgpu_set_stream(snpgpu_ctx *ctx, void *stream) {
+    if (!ctx) return SNPGPU_E_ARG;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return SNPGPU_OK;
+}
+
+int snpgpu_sync(snpgpu_ctx *ctx) {
+    if (!ctx) return SNPGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNPGPU_OK;
+}
+
+int snpgpu_host_alloc(snpgpu_ctx *ctx, size_t nbytes, void **out) {
+    if (!ctx || !out) return SNPGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostAlloc(out, nbytes ? nbytes : 1, cudaHostAllocDefault));
+    return SNPGPU_OK;
+}
+
+int snpgpu_host_free(snpgpu_ctx *ctx, void *p) {
+    if (!ctx) return SNPGPU_E_ARG;
+    if (p) CK(cudaFreeHost(p));
+    return SNPGPU_OK;
+}
+
+uint64_t snpgpu_launch_count(const snpgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ site table
+int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t *name_off, int32_t n_contigs,
+                        const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp, const int32_t *exc_contig,
+                        const int64_t *exc_pos, size_t n_exc, snpgpu_sites **out) {
+    if (!ctx || !out || n_contigs < 0) return fail(ctx, SNPGPU_E_ARG, "sites_create: bad argument");
+    if ((n_contigs && (!contig_names || !name_off)) || (n_snp && (!snp_contig || !snp_pos)) ||
+        (n_exc && (!exc_contig || !exc_pos)))
+        return fail(ctx, SNPGPU_E_ARG, "sites_create: null array");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    HostSites h;
+    const char *why = "";
+    int hrc = build_host_sites(contig_names, name_off, n_contigs, snp_contig, snp_pos, n_snp, exc_contig, exc_pos, n_exc,
+                               &h, &why);
+    if (hrc) {
+        static thread_local std::string msg;
+        msg = std::string("sites_create: ") + why;
+        return fail(ctx, hrc == 1 ? SNPGPU_E_ARG : hrc, msg.c_str());
+    }
+    const size_t n_unique = h.n_unique;
+    // one blob, 256-byte aligned sections
+    struct Sec { const void *src; size_t bytes; size_t off; };
+    std::vector<Sec> secs;
+    size_t total = 0;
+    auto add = [&](const void *src, size_t bytes) { secs.push_back({src, bytes, total}); total += (bytes + 255) & ~(size_t)255; return secs.size() - 1; };
+    size_t s_names4 = add(h.names4.data(), h.names4.size() * 4);
+    size_t s_off4 = add(h.off4.data(), h.off4.size() * 4);
+    size_t s_len1 = add(h.len1.data(), h.len1.size() * 4);
+    size_t s_names = add(h.names.data(), h.names.size());
+    size_t s_noff = add(h.name_off.data(), h.name_off.size() * 4);
+    size_t s_base = add(h.bit_base.data(), h.bit_base.size() * 8);
+    size_t s_max = add(h.max_pos.data(), h.max_pos.size() * 8);
+    size_t s_bits = add(h.bits.data(), h.bits.size() * 4);
+    size_t s_rank = add(h.rank.data(), h.rank.size() * 4);
+    size_t s_flags = add(h.flags.data(), h.flags.size());
+    size_t s_su = add(h.snp_unique.data(), h.snp_unique.size() * 4);
+    snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
+    if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create: host allocation");
+    cudaError_t e = cudaMalloc(&s->blob, total);
+    if (e != cudaSuccess) { delete s; return fail(ctx, SNPGPU_E_NOMEM, "sites_create: cudaMalloc", e); }
+    for (const Sec &x : secs) {
+        if (!x.bytes || !x.src) continue;
+        e = cudaMemcpyAsync((uint8_t *)s->blob + x.off, x.src, x.bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(s->blob); delete s; return fail(ctx, SNPGPU_E_CUDA, "sites_create: copy", e); }
+    }
+    e = cudaStreamSynchronize(ctx->stream);                      // the host vectors die with this scope
+    if (e != cudaSuccess) { cudaFree(s->blob); delete s; return fail(ctx, SNPGPU_E_CUDA, "sites_create: sync", e); }
+    auto at = [&](size_t i) { return (uint8_t *)s->blob + secs[i].off; };
+    s->ctx = ctx; s->n_snp = n_snp; s->n_unique = n_unique; s->n_contigs = n_contigs;
+    s->table.n_contigs = n_contigs; s->table.n_unique = (int32_t)n_unique;
+    s->table.names4 = (const uint32_t *)at(s_names4); s->table.off4 = (const int32_t *)at(s_off4);
+    s->table.len1 = (const int32_t *)at(s_len1); s->table.names = (const uint8_t *)at(s_names);
+    s->table.name_off = (const int32_t *)at(s_noff); s->table.bit_base = (const int64_t *)at(s_base);
+    s->table.max_pos = (const int64_t *)at(s_max); s->table.bits = (const uint32_t *)at(s_bits);
+    s->table.rank = (const uint32_t *)at(s_rank); s->table.flags = (const uint8_t *)at(s_flags);
+    s->snp_unique = (int32_t *)at(s_su);
+    *out = s;
+    return SNPGPU_OK;
+}
+
+void snpgpu_sites_destroy(snpgpu_sites *sites) {
+    if (!sites) return;
+    if (sites->ctx) { cudaSetDevice(sites->ctx->device); cudaStreamSynchronize(sites->ctx->stream); }
+    if (sites->blob) cudaFree(sites->blob);
+    delete sites;
+}
+
+size_t snpgpu_sites_n_snp(const snpgpu_sites *sites) { return sites ? sites->n_snp : 0; }
+
+// ------------------------------------------------------------------------------------------ K1
+int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
+                                const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,
+                                size_t line_out_cap, snpgpu_pileup_stats *stats_dev) {
+    if (!ctx || !sites || !params || (nbytes && !text_dev)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null argument");
+    if (mode != SNPGPU_MODE_SITES && mode != SNPGPU_MODE_ALL) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: bad mode");
+    if (((uintptr_t)text_dev & 15u) != 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text must be 16-byte aligned");
+    if (sites->n_snp && !row_out_dev) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: row_out is null");
+    if (nbytes > ((size_t)1 << 45)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text above 32 TiB");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);
+    const bool want_lines = mode == SNPGPU_MODE_ALL && line_out_dev != nullptr;
+    CK(ctx->status.ensure(sizeof(PileupStatusDev)));
+    CK(ctx->site_cells.ensure((sites->n_unique + 1) * sizeof(unsigned long long)));
+    CK(ctx->arena.ensure(ctx->arena_want));
+    if (want_lines) {
+        CK(ctx->stage.ensure((size_t)std::max(n_tiles, 1) * K1_MAXLINES * sizeof(uint16_t)));
+        CK(ctx->tile_nlines.ensure(((size_t)n_tiles + 1) * sizeof(uint32_t)));
+        CK(ctx->tile_prefix.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+    }
+    CK(cudaMemsetAsync(ctx->status.p, 0, sizeof(PileupStatusDev), st));
+    CK(cudaMemsetAsync(ctx->status.p, 0xff, sizeof(unsigned long long), st));     // first_error = ~0
+    CK(cudaMemsetAsync(ctx->site_cells.p, 0, (sites->n_unique + 1) * sizeof(unsigned long long), st));
+    PileupArgs a;
+    a.text = (const uint8_t *)text_dev;
+    a.nbytes = nbytes;
+    a.sites = sites->table;
+    memcpy(&a.p, params, sizeof(CallParams));
+    a.mode = mode;
+    a.n_tiles = n_tiles;
+    a.site_cells = (unsigned long long *)ctx->site_cells.p;
+    a.line_stage = want_lines ? (uint16_t *)ctx->stage.p : nullptr;
+    a.tile_nlines = want_lines ? (uint32_t *)ctx->tile_nlines.p : nullptr;
+    a.st = (PileupStatusDev *)ctx->status.p;
+    a.arena = (uint8_t *)ctx->arena.p;
+    a.arena_cap = ctx->arena.cap;
+    const int bps = ctx->k1_blocks[params->min_base_qual > 0 ? 1 : 0];
+    ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
+    if (sites->n_snp)
+        ctx->launches += (uint64_t)k1_launch_row(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev);
+    if (want_lines)
+        ctx->launches += (uint64_t)k1_launch_lines(st, a.line_stage, a.tile_nlines, n_tiles,
+                                                   (unsigned long long *)ctx->tile_prefix.p, line_out_dev, line_out_cap);
+    if (stats_dev) ctx->launches += (uint64_t)k1_launch_stats(st, a.st, stats_dev);
+    CK(cudaGetLastError());
+    return SNPGPU_OK;
+}
+
+int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, const snpgpu_sites *sites,
+                            const snpgpu_params *params, int mode, uint8_t *row_out, uint16_t *line_out,
+                            size_t line_out_cap, snpgpu_pileup_stats *stats) {
+    if (!ctx || !sites || !params || (nbytes && !text)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null argument");
+    if (sites->n_snp && !row_out) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: row_out is null");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
+    bool normalized = false, skip_copy = false;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->text.ensure(nbytes + 64));
+        CK(ctx->row.ensure(sites->n_snp + 16));
+        CK(ctx->stats.ensure(sizeof(snpgpu_pileup_stats)));
+        if (want_lines) CK(ctx->lines.ensure(line_out_cap * sizeof(uint16_t)));
+        if (nbytes && !skip_copy) CK(cudaMemcpyAsync(ctx->text.p, text, nbytes, cudaMemcpyHostToDevice, st));
+        int rc = snpgpu_pileup_consensus_dev(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p,
+                                             want_lines ? (uint16_t *)ctx->lines.p : nullptr, line_out_cap,
+                                             (snpgpu_pileup_stats *)ctx->stats.p);
+        if (rc) return rc;
+        snpgpu_pileup_stats hs;
+        CK(cudaMemcpyAsync(&hs, ctx->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        if (sites->n_snp) CK(cudaMemcpyAsync(row_out, ctx->row.p, sites->n_snp, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hs.error_code == SNPGPU_E_LONECR && !normalized) {   // classic-Mac line ends: universal newlines, redo
+            ctx->launches += (uint64_t)k1_launch_normalize(st, (uint8_t *)ctx->text.p, nbytes);
+            normalized = true;
+            attempt--;
+            skip_copy = true;
+            continue;
+        }
+        if (hs.error_code == SNPGPU_E_NOMEM && attempt == 0) {    // the exact-splice scratch was too small: grow, redo
+            ctx->arena_want = (size_t)hs.error_offset + (1 << 20);
+            continue;
+        }
+        if (want_lines && hs.error_code == 0) {
+            size_t n = (size_t)std::min<uint64_t>(hs.n_lines, line_out_cap);
+            if (n) CK(cudaMemcpy(line_out, ctx->lines.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        }
+        if (stats) *stats = hs;
+        if (hs.error_code) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "pileup_consensus: the reference raises (code %d) on the line at byte offset %llu",
+                     hs.error_code, (unsigned long long)hs.error_offset);
+            return fail(ctx, hs.error_code, msg);
+        }
+        return SNPGPU_OK;
+    }
+    return fail(ctx, SNPGPU_E_NOMEM, "pileup_consensus: splice scratch");
+}
+
+int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes) {
+    if (!ctx || (nbytes && !text_dev)) return fail(ctx, SNPGPU_E_ARG, "normalize_newlines: null argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches += (uint64_t)k1_launch_normalize(ctx->stream, (uint8_t *)text_dev, nbytes);
+    CK(cudaGetLastError());
+    return SNPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+int snpgpu_merge_sites_dev(snpgpu_ctx *ctx, const uint64_t *keys_dev, const uint32_t *sample_of_dev, size_t n,
+                           uint64_t *uniq_out_dev, uint32_t *count_out_dev, uint32_t *samples_out_dev,
+                           size_t *n_uniq_out) {
+    if (!ctx || !n_uniq_out || (n && (!keys_dev || !sample_of_dev || !uniq_out_dev || !count_out_dev || !samples_out_dev)))
+        return fail(ctx, SNPGPU_E_ARG, "merge_sites: null argument");
+    if (n >= ((size_t)1 << 31)) return fail(ctx, SNPGPU_E_ARG, "merge_sites: more than 2^31 keys");
+    CK(cudaSetDevice(ctx->device));
+    size_t tb = k2_workspace_bytes(n);
+    CK(ctx->k2_tmp.ensure(tb));
+    CK(ctx->k2_n.ensure(sizeof(unsigned long long)));
+    int launches = 0;
+    int rc = k2_launch(ctx->stream, keys_dev, sample_of_dev, n, uniq_out_dev, count_out_dev, samples_out_dev,
+                       (unsigned long long *)ctx->k2_n.p, ctx->k2_tmp.p, ctx->k2_tmp.cap, &launches);
+    if (rc) return fail(ctx, rc, "merge_sites: sort / run-length encode failed");
+    ctx->launches += (uint64_t)launches;
+    unsigned long long nu = 0;
+    CK(cudaMemcpyAsync(&nu, ctx->k2_n.p, sizeof(nu), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_uniq_out = (size_t)nu;
+    return SNPGPU_OK;
+}
+
+int snpgpu_merge_sites(snpgpu_ctx *ctx, const uint64_t *keys, const uint32_t *sample_of, size_t n, uint64_t *uniq_out,
+                       uint32_t *count_out, uint32_t *samples_out, size_t *n_uniq_out) {
+    if (!ctx || !n_uniq_out || (n && (!keys || !sample_of || !uniq_out || !count_out || !samples_out)))
+        return fail(ctx, SNPGPU_E_ARG, "merge_sites: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) { *n_uniq_out = 0; return SNPGPU_OK; }
+    CK(ctx->k2_keys.ensure(n * 8)); CK(ctx->k2_samp.ensure(n * 4)); CK(ctx->k2_uniq.ensure(n * 8));
+    CK(ctx->k2_cnt.ensure(n * 4)); CK(ctx->k2_out.ensure(n * 4));
+    CK(cudaMemcpyAsync(ctx->k2_keys.p, keys, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->k2_samp.p, sample_of, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = snpgpu_merge_sites_dev(ctx, (const uint64_t *)ctx->k2_keys.p, (const uint32_t *)ctx->k2_samp.p, n,
+                                    (uint64_t *)ctx->k2_uniq.p, (uint32_t *)ctx->k2_cnt.p, (uint32_t *)ctx->k2_out.p,
+                                    n_uniq_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(uniq_out, ctx->k2_uniq.p, *n_uniq_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(count_out, ctx->k2_cnt.p, *n_uniq_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(samples_out, ctx->k2_out.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K4
+int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
+                                 size_t row_stride, size_t row_begin, size_t row_end, int32_t *dist_out_dev) {
+    if (!ctx || (n_rows && n_sites && !matrix_dev) || (n_rows && !dist_out_dev))
+        return fail(ctx, SNPGPU_E_ARG, "pairwise_distance: null argument");
+    if (row_stride < n_sites || row_begin > row_end || row_end > n_rows)
+        return fail(ctx, SNPGPU_E_ARG, "pairwise_distance: bad stride or row range");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->k4_tmp.ensure(k4_workspace_bytes(n_rows, n_sites)));
+    int launches = 0;
+    int rc = k4_launch(ctx->stream, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, dist_out_dev,
+                       ctx->k4_tmp.p, &launches);
+    if (rc) return fail(ctx, rc, "pairwise_distance: launch failed");
+    ctx->launches += (uint64_t)launches;
+    return SNPGPU_OK;
+}
+
+int snpgpu_pairwise_distance(snpgpu_ctx *ctx, const uint8_t *matrix, size_t n_rows, size_t n_sites, size_t row_stride,
+                             int32_t *dist_out) {
+    if (!ctx || (n_rows && n_sites && !matrix) || (n_rows && !dist_out))
+        return fail(ctx, SNPGPU_E_ARG, "pairwise_distance: null argument");
+    if (row_stride < n_sites) return fail(ctx, SNPGPU_E_ARG, "pairwise_distance: row_stride < n_sites");
+    if (n_rows == 0) return SNPGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t mb = n_rows * row_stride, db = n_rows * n_rows * sizeof(int32_t);
+    CK(ctx->k4_mat.ensure(mb + 64));
+    CK(ctx->k4_dist.ensure(db));
+    if (mb) CK(cudaMemcpyAsync(ctx->k4_mat.p, matrix, mb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = snpgpu_pairwise_distance_dev(ctx, (const uint8_t *)ctx->k4_mat.p, n_rows, n_sites, row_stride, 0, n_rows,
+                                          (int32_t *)ctx->k4_dist.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dist_out, ctx->k4_dist.p, db, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNPGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ synthetic input
+int snpgpu_synth_pileup_dev(snpgpu_ctx *ctx, const snpgpu_synth_spec *spec, const char *contig_name, void *text_dev,
+                            size_t cap, size_t *nbytes_out) {
+    if (!ctx || !spec || !contig_name || !text_dev || !nbytes_out) return fail(ctx, SNPGPU_E_ARG, "synth: null argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t tb = synth_workspace_bytes(spec->genome_len);
+    CK(ctx->synth_tmp.ensure(tb));
+    CK(ctx->synth_n.ensure(sizeof(unsigned long long)));
+    int launches = 0;
+    int rc = synth_launch(ctx->stream, *spec, contig_name, (uint8_t *)text_dev, cap, (unsigned long long *)ctx->synth_n.p,
+                          ctx->synth_tmp.p, ctx->synth_tmp.cap, &launches);
+    if (rc) return fail(ctx, rc, "synth: launch failed");
+    ctx->launches += (uint64_t)launches;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->synth_n.p, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *nbytes_out = (size_t)n;
+    if (n > cap) return fail(ctx, SNPGPU_E_NOMEM, "synth: text buffer too small");
+    return SNPGPU_OK;
+}
+
+int snpgpu_synth_sample_sites(snpgpu_ctx *ctx, const snpgpu_synth_spec *spec, uint32_t *pos_out, size_t cap,
+                              size_t *n_out) {
+    if (!spec || !n_out || (cap && !pos_out)) return fail(ctx, SNPGPU_E_ARG, "synth_sample_sites: null argument");
+    synth_host_sites(*spec, pos_out, cap, n_out);
+    return SNPGPU_OK;
+}
+
+}  // extern "C"

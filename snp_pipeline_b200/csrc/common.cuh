@@ -1,0 +1,85 @@
+// common.cuh -- shared device-side structures and PTX helpers of libsnpgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/snpgpu.h"
+#include "hd.cuh"
+#include "sites.cuh"
+
+namespace snpgpu {
+
+// Device-side status of one pileup call.  first_error orders errors by file offset so the one reported is
+// the one the reference would have raised first.
+struct PileupStatusDev {
+    unsigned long long first_error;   // (byte offset of the line << 8) | code ; ~0 when clean (atomicMin)
+    unsigned long long n_lines;
+    unsigned long long n_parsed;
+    unsigned long long n_general;
+    unsigned long long arena_used;    // bytes of scratch claimed by the exact-splice path
+    unsigned int       arena_overflow;
+    unsigned int       pad;
+};
+
+// Tile geometry of the pileup kernel.
+constexpr int K1_TILE     = 32768;             // bytes of text whose line starts one tile owns
+constexpr int K1_LOOK     = 2048;              // extra bytes staged so that the last owned line is complete
+constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
+constexpr int K1_THREADS  = 256;
+constexpr int K1_WARPS    = K1_THREADS / 32;
+constexpr int K1_WREGION  = K1_TILE / K1_WARPS;      // bytes scanned for newlines by one warp
+constexpr int K1_WCAP     = 128;               // line starts a warp records per pass (more -> another pass)
+constexpr int K1_GENQ     = 128;               // fallback lines queued per pass before they run inline
+constexpr int K1_MAXLINES = K1_TILE / 8;       // all-positions mode: a line that parses has >= 8 bytes
+
+struct PileupArgs {
+    const uint8_t      *text;          // 16-byte aligned
+    unsigned long long  nbytes;
+    SiteTable           sites;
+    CallParams          p;
+    int                 mode;          // SNPGPU_MODE_SITES / SNPGPU_MODE_ALL
+    int                 n_tiles;
+    unsigned long long *site_cells;    // n_unique, zero-initialised: ((line offset + 1) << 8) | cell  (atomicMax:
+                                       // the last line in file order wins, like the dict of call_consensus.py:169)
+    uint16_t           *line_stage;    // [n_tiles][K1_MAXLINES] or null: cell | fail << 8 per line of the tile
+    uint32_t           *tile_nlines;   // [n_tiles] or null
+    PileupStatusDev    *st;
+    uint8_t            *arena;
+    unsigned long long  arena_cap;
+};
+
+// ---- PTX: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared, bytes a multiple of 16, both addresses 16-byte aligned; completion lands on bar
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace snpgpu

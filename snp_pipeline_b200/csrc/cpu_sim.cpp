@@ -1,0 +1,113 @@
+// cpu_sim.cpp -- TEST HARNESS ONLY (tests/test_cpu_sim.py); never loaded by the product package.
+//
+// Compiles the very same per-line parsers the kernel runs (line_fast.cuh, line_general.cuh, sites.cuh) with g++ and
+// drives them over a text the way k1_pileup.cu does -- '\n'-delimited lines, fast parser first, the exact parser
+// for whatever it declines, last-line-wins per site -- so that their logic can be checked against the oracle in
+// the build container, which has no GPU.  The tile/scan machinery of the kernel is GPU-only and is covered by the
+// -m gpu tests.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "line_fast.cuh"
+#include "line_general.cuh"
+#include "sites_host.h"
+
+using namespace snpgpu;
+
+extern "C" {
+
+// counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code
+int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, const int32_t *name_off,
+                  int32_t n_contigs, const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp,
+                  const int32_t *exc_contig, const int64_t *exc_pos, size_t n_exc, const CallParams *p, int all_positions,
+                  int force_general, uint8_t *row_out, uint16_t *line_out, size_t line_out_cap, uint64_t *counters) {
+    HostSites h;
+    const char *why;
+    int rc = build_host_sites(contig_names, name_off, n_contigs, snp_contig, snp_pos, n_snp, exc_contig, exc_pos, n_exc,
+                              &h, &why);
+    if (rc) return 100 + rc;
+    SiteTable t = h.view();
+    std::vector<uint64_t> cells(h.n_unique + 1, 0);
+    // staging copy: 4-byte aligned, '\n' sentinels behind the text (what the kernel's shared-memory window looks like)
+    std::vector<uint32_t> store((nbytes + 64) / 4 + 4, 0x0a0a0a0au);
+    uint8_t *buf = reinterpret_cast<uint8_t *>(store.data());
+    memcpy(buf, text, nbytes);
+    memset(buf + nbytes, '\n', 48);
+    // classic-Mac line ends: what snpgpu_normalize_newlines_dev does before the kernel is run again (api.cu)
+    for (size_t i = 0; i < nbytes; i++)
+        if (buf[i] == '\r' && buf[i + 1] != '\n') buf[i] = '\n';
+    uint64_t n_lines = 0, n_parsed = 0, n_general = 0;
+    int hint = 0;
+    size_t s = 0;
+    counters[3] = ~0ull; counters[4] = 0;
+    std::vector<uint8_t> scratch;
+    while (s < nbytes) {
+        size_t e = s;
+        bool high = false, lone_cr = false;
+        while (e < nbytes && buf[e] != '\n') {
+            if (buf[e] >= 0x80) high = true;
+            if (buf[e] == '\r' && e + 1 < nbytes && buf[e + 1] != '\n') lone_cr = true;
+            e++;
+        }
+        const size_t line_idx = n_lines++;
+        int st = ST_FALLBACK;
+        FastLine fl;
+        if (!force_general && !high) {
+            if (p->min_base_qual > 0) st = fast_line<true>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);
+            else st = fast_line<false>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);
+        }
+        unsigned base = 0, fail = 0;
+        int32_t site = -1;
+        bool have = false;
+        if (st == ST_OK) { base = fl.base; fail = fl.fail; site = fl.site; have = true; }
+        else if (st == ST_FALLBACK) {
+            n_general++;
+            int err = 0;
+            LineCall r;
+            const uint8_t *line = buf + s;
+            int64_t n = (int64_t)(e - s);
+            if (lone_cr) err = ST_DOMAIN;
+            bool wanted = true;
+            if (!err && !all_positions) {
+                general_key(line, n, &r);
+                err = r.status;
+                if (!err) {
+                    site = site_find(t, contig_find(t, line + r.chrom_off, r.chrom_len), r.pos);
+                    wanted = site >= 0;
+                }
+            }
+            if (!err && wanted) {
+                general_line(line, n, *p, nullptr, 0, &r);
+                if (r.status == ST_NEED_ARENA) {
+                    scratch.resize((size_t)r.bases_len + 16);
+                    general_line(line, n, *p, scratch.data(), r.bases_len, &r);
+                }
+                err = r.status;
+                if (!err) {
+                    if (all_positions) site = site_find(t, contig_find(t, line + r.chrom_off, r.chrom_len), r.pos);
+                    base = r.base; fail = r.fail; have = true;
+                }
+            }
+            if (err) { counters[3] = s; counters[4] = (uint64_t)err; break; }
+        }
+        if (have) {
+            unsigned flags = site >= 0 ? h.flags[site] : 0u;
+            if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
+            unsigned cell = (fail || base == '*') ? (unsigned)'-' : base;
+            if (flags & SITE_SNP) cells[site] = ((uint64_t)(s + 1) << 8) | cell;
+            if (line_out && line_idx < line_out_cap) line_out[line_idx] = (uint16_t)(cell | (fail << 8));
+            n_parsed++;
+        } else if (line_out && all_positions && line_idx < line_out_cap) {
+            line_out[line_idx] = 0;
+        }
+        s = e + 1;
+    }
+    for (size_t k = 0; k < n_snp; k++) {
+        uint64_t c = cells[h.snp_unique[k]];
+        row_out[k] = c ? (uint8_t)(c & 0xff) : (uint8_t)'-';
+    }
+    counters[0] = n_lines; counters[1] = n_parsed; counters[2] = n_general;
+    return (int)counters[4];
+}
+
+}  // extern "C"

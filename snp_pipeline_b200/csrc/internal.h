@@ -1,0 +1,37 @@
+// internal.h -- launchers shared between the translation units of libsnpgpu (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace snpgpu {
+
+// k1_pileup.cu
+size_t k1_smem_bytes();
+int    k1_blocks_per_sm(bool has_qual);
+// enqueue the pileup kernel over `a`; returns the number of kernels launched
+int    k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks);
+int    k1_launch_row(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique,
+                     size_t n_snp, uint8_t *row_out_dev);
+int    k1_launch_lines(cudaStream_t stream, const uint16_t *line_stage, const uint32_t *tile_nlines, int n_tiles,
+                       unsigned long long *tile_prefix, uint16_t *line_out_dev, size_t line_out_cap);
+int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
+int    k1_launch_stats(cudaStream_t stream, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev);
+
+// k2_merge.cu
+// sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller
+size_t k2_workspace_bytes(size_t n);
+int    k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *sample_of, size_t n, uint64_t *uniq_out,
+                 uint32_t *count_out, uint32_t *samples_out, unsigned long long *n_uniq_dev, void *tmp,
+                 size_t tmp_bytes, int *launches);
+
+// k4_distance.cu
+size_t k4_workspace_bytes(size_t n_rows, size_t n_sites);
+int    k4_launch(cudaStream_t stream, const uint8_t *matrix, size_t n_rows, size_t n_sites, size_t row_stride,
+                 size_t row_begin, size_t row_end, int32_t *dist_out, void *tmp, int *launches);
+
+// synth.cu
+int    synth_launch(cudaStream_t stream, const snpgpu_synth_spec &spec, const char *contig_name, uint8_t *text_dev,
+                    size_t cap, unsigned long long *nbytes_dev, void *tmp, size_t tmp_bytes, int *launches);
+size_t synth_workspace_bytes(uint32_t genome_len);
+void   synth_host_sites(const snpgpu_synth_spec &spec, uint32_t *pos_out, size_t cap, size_t *n_out);
+
+}  // namespace snpgpu

@@ -1,0 +1,367 @@
+"""Parity of the CUDA path (through the C ABI, libsnpgpu.so) with the oracle -- the `-m gpu` tests proper.
+
+Bit-exact: consensus rows, per-line cells and fail masks, first-error codes and offsets, merged site lists, distance
+matrices.  Inputs: the reference's bundled lambda-virus / Agona / Listeria files (tests/golden), the golden vectors
+produced by the reference's own Python (ref_files), seeded synthetic texts (tests/linegen.py) and device-generated
+pileups at BASELINE.json's sample size.
+"""
+import ctypes
+import os
+import random
+
+import numpy as np
+import pytest
+
+import linegen
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+PARAM_SETS = [(0, 0.6, 1, 0, 0.0), (0, 0.6, 3, 0, 0.0), (15, 0.6, 3, 1, 0.1), (0, 0.55, 2, 2, 0.25),
+              (20, 0.9, 10, 0, 0.5), (0, 1.0, 0, 0, 0.0), (-5, 0.51, 1, 3, 0.33)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from snp_pipeline_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _gpu_params(ps):
+    from snp_pipeline_b200 import _lib
+    return _lib.make_params(*ps)
+
+
+def _line_offsets(text):
+    """byte offset of every line start under universal newlines"""
+    offs, i, n = [], 0, len(text)
+    while i < n:
+        offs.append(i)
+        j = i
+        while j < n and text[j] not in (10, 13):
+            j += 1
+        if j < n and text[j] == 13 and j + 1 < n and text[j + 1] == 10:
+            j += 1
+        i = j + 1
+    return offs
+
+
+def _compare(ctx, text, snps, excl, ps, all_pos):
+    from snp_pipeline_b200 import _lib
+    op = orc.make_params(*ps)
+    want_err = 0
+    try:
+        want_row, (cells, fails, _) = orc.pileup_consensus(text, snps, excl, op, parse_all=all_pos, want_lines=True)
+    except orc.OracleError as e:
+        want_err, err_line = e.status, e.line
+    sites = ctx.sites(snps, excl)
+    try:
+        mode = _lib.MODE_ALL if all_pos else _lib.MODE_SITES
+        try:
+            out = ctx.pileup_consensus(text, sites, _gpu_params(ps), mode, want_lines=all_pos)
+        except _lib.SnpGpuError as e:
+            assert want_err and e.code == want_err, (e.code, want_err, str(e))
+            assert e.offset == _line_offsets(text)[err_line]
+            return None
+        assert not want_err, "the oracle raises (%d) and the kernel does not" % want_err
+        row, stats = out[0], out[1]
+        assert row == want_row
+        assert stats.n_lines == len(_line_offsets(text))
+        if all_pos:
+            lines = out[2]
+            assert len(lines) == len(cells)
+            assert np.array_equal(lines & 0xff, cells)
+            assert np.array_equal(lines >> 8, fails)
+        else:
+            assert stats.n_parsed == len(cells)
+        return stats
+    finally:
+        sites.close()
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("branch", ["", "_preserved"])
+def test_lambda_golden(ctx, golden_dir, branch):
+    """BASELINE config 1: the bundled lambda-virus pileups -> consensus.fasta, byte for byte."""
+    from snp_pipeline_b200 import _lib
+    root = os.path.join(golden_dir, "lambda")
+    snps = orc.read_snp_list(os.path.join(root, "snplist%s.txt" % branch))
+    p = _lib.make_params(min_cons_depth=3)
+    for s in ("sample1", "sample2", "sample3", "sample4"):
+        sdir = os.path.join(root, "samples", s)
+        text = open(os.path.join(sdir, "reads.all.pileup"), "rb").read()
+        excl = orc.vcf_sites(os.path.join(sdir, "var.flt_removed.vcf")) if branch else []
+        sites = ctx.sites(snps, excl)
+        golden = open(os.path.join(sdir, "consensus%s.fasta" % branch)).read()
+        for mode in (_lib.MODE_SITES, _lib.MODE_ALL):
+            row, stats = ctx.pileup_consensus(text, sites, p, mode)[:2]
+            assert orc.fasta_text(s, row.decode()) == golden
+            assert stats.n_lines == 48502
+            assert stats.n_general < 200, "lambda lines should stay on the fast path"
+        sites.close()
+        _compare(ctx, text, snps, excl, (0, 0.6, 3, 0, 0.0), True)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_realistic_text(ctx, seed):
+    rng = random.Random(seed)
+    n = 20000 if seed < 2 else 3000
+    sites = {p: rng.choice("ACGT") for p in rng.sample(range(1, n + 1), 200)}
+    text = linegen.pileup_text(seed, n, sites=sites, gaps=0.01).encode()
+    snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 40), 300))]
+    excl = [(linegen.CHROM, p) for p in rng.sample(range(1, n), 40)] if seed % 2 else []
+    ps = PARAM_SETS[seed % len(PARAM_SETS)]
+    for all_pos in (False, True):
+        st = _compare(ctx, text, snps, excl, ps, all_pos)
+        assert st.n_general < st.n_lines * 0.02 + 5
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_nasty_text(ctx, seed):
+    """Legal-but-odd lines (caret chains, odd indel tokens, IUPAC, short quality strings, odd separators, lines the
+    reference raises on): values, error codes and error offsets."""
+    rng = random.Random(100 + seed)
+    n = 900
+    text = linegen.pileup_text(200 + seed, n, nasty=0.5).encode()
+    if seed % 2 == 0:      # keep half of the seeds on the value path: drop the lines the reference raises on
+        op = orc.make_params()
+        text = b"".join(ln + b"\n" for ln in text.split(b"\n")[:-1] if orc.line_report(ln, op)["status"] == 0)
+    if seed % 3 == 0:
+        text = text.replace(b"\r\n", b"\n").replace(b"\n", b"\r\n")
+    if seed % 4 == 1:
+        text = text[:-1]
+    snps = [(linegen.CHROM, p) for p in rng.sample(range(1, n + 10), 300)]
+    excl = [(linegen.CHROM, p) for p in rng.sample(range(1, n), 30)]
+    for ps in (PARAM_SETS[seed % len(PARAM_SETS)], PARAM_SETS[(seed + 2) % len(PARAM_SETS)]):
+        for all_pos in (False, True):
+            _compare(ctx, text, snps, excl, ps, all_pos)
+
+
+def test_reference_file_vectors(ctx, ref_files):
+    """Vectors produced by the reference's own `call_consensus` (tests/golden/make_golden.py)."""
+    from snp_pipeline_b200 import _lib
+    exc = {_lib.E_VALUE: "ValueError", _lib.E_INDEX: "IndexError", _lib.E_UNPACK: "ValueError"}
+    n_ok = n_raise = 0
+    for case in ref_files:
+        snps = [(ln.split()[0], int(ln.split()[1])) for ln in case["snplist"].splitlines()]
+        excl = []
+        if case["exclude"]:
+            for ln in case["exclude"].splitlines():
+                if not ln.startswith("#"):
+                    f = ln.split("\t")
+                    excl.append((f[0], int(f[1])))
+        sites = ctx.sites(snps, excl)
+        mode = _lib.MODE_ALL if case["all_pos"] else _lib.MODE_SITES
+        ref = case["ref"]
+        try:
+            row = ctx.pileup_consensus(case["pileup"].encode(), sites, _gpu_params(case["params"]), mode)[0]
+            assert ref["exit"] == 0
+            assert orc.fasta_text("sampleX", row.decode()) == ref["fasta"]
+            n_ok += 1
+        except _lib.SnpGpuError as e:
+            assert exc[e.code] == str(ref["exit"]).split(":")[1]
+            n_raise += 1
+        sites.close()
+    assert n_ok >= 20 and n_raise >= 20
+
+
+def test_edge_inputs(ctx):
+    from snp_pipeline_b200 import _lib
+    p = _lib.make_params()
+    snps = [(linegen.CHROM, 5), (linegen.CHROM, 7), ("other", 1)]
+    sites = ctx.sites(snps)
+    # empty file: every cell is '-'
+    row, stats = ctx.pileup_consensus(b"", sites, p)
+    assert row == b"---" and stats.n_lines == 0
+    # a single line without terminator
+    line = ("%s\t5\tA\t3\tGGg\tIII" % linegen.CHROM).encode()
+    row, stats = ctx.pileup_consensus(line, sites, p)
+    assert row == b"G--" and stats.n_lines == 1
+    # empty snplist is fine (regression_tests.sh:3156-3211)
+    empty = ctx.sites([])
+    row, stats = ctx.pileup_consensus(line + b"\n", empty, p)
+    assert row == b""
+    row, stats, lines = ctx.pileup_consensus(line + b"\n", empty, p, _lib.MODE_ALL, want_lines=True)
+    assert len(lines) == 1 and chr(lines[0] & 0xff) == "G"
+    empty.close()
+    # a very deep line (longer than the kernel's staging look-ahead) goes through the exact path
+    deep = ("%s\t7\tC\t9000\t%s\t%s\n" % (linegen.CHROM, "." * 4000 + "t" * 5000, "I" * 9000)).encode()
+    text = line + b"\n" + deep
+    _compare(ctx, text, snps, [], (0, 0.55, 1, 0, 0.0), True)
+    _compare(ctx, text, snps, [], (0, 0.55, 1, 0, 0.0), False)
+    # many tiny lines in one tile (more line starts than one scan pass records)
+    tiny = b"".join(b"c %d\n" % i for i in range(30000))
+    row, stats = ctx.pileup_consensus(tiny, sites, p)
+    assert row == b"---" and stats.n_lines == 30000
+    # classic-Mac line ends: universal newlines (pileup.py:417)
+    mac = linegen.pileup_text(3, 400).replace("\n", "\r").encode()
+    _compare(ctx, mac, [(linegen.CHROM, q) for q in range(1, 400, 7)], [], (0, 0.6, 1, 0, 0.0), False)
+    _compare(ctx, mac, [(linegen.CHROM, q) for q in range(1, 400, 7)], [], (0, 0.6, 1, 0, 0.0), True)
+    # non-ASCII byte: outside the byte domain, reported at its line
+    bad = linegen.pileup_text(4, 50).encode()
+    offs = _line_offsets(bad)
+    bad2 = bad[:offs[20] + 3] + b"\xc3" + bad[offs[20] + 4:]
+    with pytest.raises(_lib.SnpGpuError) as ei:
+        ctx.pileup_consensus(bad2, sites, p)
+    assert ei.value.code == _lib.E_DOMAIN and ei.value.offset == offs[20]
+    sites.close()
+
+
+def test_multi_contig_and_duplicates(ctx):
+    rng = random.Random(11)
+    chroms = ["chrB|x", "chrA", "chr10"]
+    parts, allpos = [], []
+    for c in chroms:
+        n = 2500
+        parts.append(linegen.pileup_text(len(c), n, chrom=c, gaps=0.02))
+        allpos += [(c, q) for q in range(1, n + 100)]
+    text = "".join(parts)
+    lines = text.splitlines(True)
+    text = "".join(lines + lines[100:140][::-1]).encode()       # repeated positions: the last line wins
+    snps = rng.sample(allpos, 400)
+    snps = snps + snps[:7]                                      # duplicates in the snplist are emitted twice
+    excl = rng.sample(allpos, 60)
+    for all_pos in (False, True):
+        _compare(ctx, text, snps, excl, (0, 0.6, 2, 0, 0.0), all_pos)
+
+
+def _synth(ctx, genome_len, sample, pool, carry=0.05, seed=20261017):
+    import torch
+    from snp_pipeline_b200 import _lib
+    spec = _lib.SynthSpec(seed, sample, genome_len, 24, pool, carry, 0.0)
+    cap = int(genome_len) * 112 + 4096
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.synth_pileup_dev(spec, "gi|0000000|ref|SYN_5000K.1|", buf.data_ptr(), cap)
+    return spec, buf, n
+
+
+@pytest.mark.parametrize("genome_len,sample", [(200000, 0), (5000000, 3)])
+def test_synthetic_sample_device_resident(ctx, genome_len, sample):
+    """BASELINE config 2's unit of work: one synthetic sample (5 Mbp at the full size), text resident in HBM,
+    through the device-pointer entry point; every line's cell and fail mask against the oracle."""
+    import torch
+    from snp_pipeline_b200 import _lib
+    spec, buf, n = _synth(ctx, genome_len, sample, pool=genome_len // 100)
+    assert 80 * genome_len < n < 100 * genome_len
+    chrom = "gi|0000000|ref|SYN_5000K.1|"
+    own = ctx.synth_sample_sites(spec)
+    assert len(own) > 0
+    rng = random.Random(sample)
+    extra = rng.sample(range(1, genome_len + 1), 2000)
+    snps = sorted({(chrom, int(q)) for q in own} | {(chrom, q) for q in extra}, key=lambda t: t[1])
+    sites = ctx.sites(snps)
+    p = _lib.make_params(min_cons_depth=3)
+    row = torch.empty(len(snps), dtype=torch.uint8, device="cuda")
+    lines = torch.empty(genome_len + 8, dtype=torch.int16, device="cuda")
+    stats = torch.zeros(5, dtype=torch.int64, device="cuda")
+    text = buf[:n].cpu().numpy()
+    op = orc.make_params(min_cons_depth=3)
+    want_row, (cells, fails, _) = orc.pileup_consensus(text, snps, [], op, parse_all=True, want_lines=True)
+    for mode in (_lib.MODE_ALL, _lib.MODE_SITES):
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.pileup_consensus_dev(buf.data_ptr(), n, sites, p, mode, row.data_ptr(), lines.data_ptr(), genome_len + 8,
+                                 stats.data_ptr())
+        torch.cuda.synchronize()
+        st = stats.cpu().numpy()
+        assert st[0] == genome_len and st[4] == 0
+        assert row.cpu().numpy().tobytes() == want_row
+        if mode == _lib.MODE_ALL:
+            got = lines[:genome_len].cpu().numpy().view(np.uint16)
+            assert np.array_equal(got & 0xff, cells)
+            assert np.array_equal(got >> 8, fails)
+            assert st[2] < genome_len * 0.01      # indel-odd lines only
+        else:
+            assert st[1] == len(snps)
+    # the variant cells really are variant: most carried sites call the alternate allele
+    called = sum(1 for (c, q), b in zip(snps, want_row) if q in set(int(x) for x in own) and chr(b) in "ACGT")
+    assert called > 0.8 * len(own)
+    ctx.set_stream(None)
+    sites.close()
+
+
+# ------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("dataset,vcf", [("lambda", "var.flt.vcf"), ("agona", "var.flt.vcf"),
+                                         ("listeria", "var.flt.vcf")])
+def test_merge_sites_golden(ctx, golden_dir, dataset, vcf):
+    root = os.path.join(golden_dir, dataset)
+    names = sorted(os.listdir(os.path.join(root, "samples")))
+    per = [orc.vcf_sites(os.path.join(root, "samples", n, vcf)) for n in names]
+    chroms = sorted({c for s in per for c, _ in s})
+    rank = {c: i for i, c in enumerate(chroms)}
+    keys = np.array([(rank[c] << 32) | p for s in per for c, p in s], dtype=np.uint64)
+    samp = np.array([i for i, s in enumerate(per) for _ in s], dtype=np.uint32)
+    uniq, cnt, samples = ctx.merge_sites(keys, samp)
+    lines, o = [], 0
+    for k, c in zip(uniq, cnt):
+        who = [names[i] for i in samples[o:o + c]]
+        o += int(c)
+        lines.append("%s\t%d\t%d\t%s\n" % (chroms[int(k) >> 32], int(k) & 0xffffffff, c, "\t".join(who)))
+    assert "".join(lines) == open(os.path.join(root, "snplist.txt")).read()
+
+
+@pytest.mark.parametrize("n_samples,per_sample,seed", [(1, 1, 0), (3, 0, 1), (100, 500, 2), (1000, 5000, 3)])
+def test_merge_sites_random(ctx, n_samples, per_sample, seed):
+    rng = np.random.default_rng(seed)
+    keys, samp = [], []
+    for s in range(n_samples):
+        k = rng.choice(200000, size=per_sample, replace=False).astype(np.uint64) if per_sample else np.zeros(0, np.uint64)
+        k |= rng.integers(0, 3, size=k.size).astype(np.uint64) << np.uint64(32)
+        k = np.unique(k)
+        rng.shuffle(k)
+        keys.append(k)
+        samp.append(np.full(k.size, s, dtype=np.uint32))
+    keys, samp = np.concatenate(keys), np.concatenate(samp)
+    wu, wc, ws = orc.merge_sites_keys(keys, samp)
+    gu, gc, gs = ctx.merge_sites(keys, samp)
+    assert np.array_equal(wu, gu) and np.array_equal(wc, gc) and np.array_equal(ws, gs)
+    assert np.all(gu[1:] > gu[:-1])                              # sortedness, uniqueness
+    assert int(gc.sum()) == keys.size
+
+
+# ------------------------------------------------------------------------------------------ K4
+@pytest.mark.parametrize("dataset,suffix", [("lambda", ""), ("lambda", "_preserved"), ("agona", ""), ("listeria", ""),
+                                            ("listeria", "_preserved")])
+def test_distance_golden(ctx, golden_dir, dataset, suffix):
+    root = os.path.join(golden_dir, dataset)
+    seqs = orc.read_fasta_matrix(os.path.join(root, "snpma%s.fasta" % suffix))
+    ids = sorted(seqs)
+    m = np.frombuffer("".join(seqs[i] for i in ids).encode(), dtype=np.uint8).reshape(len(ids), -1)
+    d = ctx.pairwise_distance(m)
+    mat = ["\t%s\n" % "\t".join(ids)]
+    for i, a in enumerate(ids):
+        mat.append("%s\t%s\n" % (a, "\t".join(str(int(x)) for x in d[i])))
+    assert "".join(mat) == open(os.path.join(root, "snp_distance_matrix%s.tsv" % suffix)).read()
+
+
+@pytest.mark.parametrize("n,s,seed", [(1, 10, 0), (2, 0, 1), (2, 1, 2), (5, 31, 3), (7, 32, 4), (64, 33, 5), (65, 1025, 6),
+                                      (130, 3000, 7), (300, 20011, 8)])
+def test_distance_random(ctx, n, s, seed):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTACGTACGTacgt-NnRY*.", dtype=np.uint8)
+    m = alphabet[rng.integers(0, alphabet.size, size=(n, s))] if s else np.zeros((n, 0), np.uint8)
+    if s and n > 2:      # related rows so that distances are not all ~ 3/4 s
+        m[1] = m[0]
+        m[2, : s // 2] = m[0, : s // 2]
+    want = orc.distance_matrix([bytes(r) for r in m]) if s else np.zeros((n, n), np.int32)
+    got = ctx.pairwise_distance(m)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, got.T) and not got.diagonal().any()
+
+
+def test_distance_stripes(ctx):
+    """The multi-GPU sharding of K4: row stripes computed separately equal the full matrix."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, s = 203, 5000
+    m = np.frombuffer(b"ACGT-N", dtype=np.uint8)[rng.integers(0, 6, size=(n, s))]
+    full = ctx.pairwise_distance(m)
+    md = torch.from_numpy(m).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    for lo, hi in [(0, 70), (70, 128), (128, 203), (13, 14)]:
+        out = torch.zeros((hi - lo, n), dtype=torch.int32, device="cuda")
+        ctx.pairwise_distance_dev(md.data_ptr(), n, s, s, lo, hi, out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), full[lo:hi])
+    ctx.set_stream(None)
