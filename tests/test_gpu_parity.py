@@ -275,7 +275,8 @@ def test_synthetic_sample_device_resident(ctx, genome_len, sample):
         else:
             assert st[1] == len(snps)
     # the variant cells really are variant: most carried sites call the alternate allele
-    called = sum(1 for (c, q), b in zip(snps, want_row) if q in set(int(x) for x in own) and chr(b) in "ACGT")
+    own_set = set(int(x) for x in own)
+    called = sum(1 for (c, q), b in zip(snps, want_row) if q in own_set and chr(b) in "ACGT")
     assert called > 0.8 * len(own)
     ctx.set_stream(None)
     sites.close()
