@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path (site union -> pileup parse + tally + consensus -> SNP matrix -> pairwise distance) on
+BASELINE.json's configuration 2: synthetic 100 samples x 5 Mbp reference, ~50 k SNP sites, per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one pass of the whole path over the rank's batch of samples:
+    K2 union of the samples' variant-site lists          (merge_sites)
+    K1 every pileup line parsed, tallied, called         (call_consensus --vcfAllPos: all-positions mode, so no
+       + K3 gather into the samples x sites matrix        line is skipped), 2 B of result per line + the matrix row
+    K4 all-pairs distance over the matrix                 (distance)
+`value` times that with the pileup text resident in HBM (100 samples = 44.5 GB, far above L2, so no flush is
+needed); `e2e` times the same path through the host-buffer C-ABI calls (pinned host text -> H2D inside the timed
+region, results read back every step).  Multi-GPU: samples are sharded per rank (weak scaling: 100 per GPU), one NCCL
+all-gather of the per-rank site lists and one of the matrix rows; each rank computes its stripe of the distances.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of
+the same workload.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONTIG = "gi|0000000|ref|SYN_5000K.1|"
+SEED = 20261017
+METRIC = "pileup positions/sec through site-union + parse/tally/consensus + SNP-matrix + pairwise distance"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=100, help="samples per GPU")
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--pool-sites", type=int, default=50_000)
+    ap.add_argument("--carry", type=float, default=0.05)
+    ap.add_argument("--host-pool", type=int, default=4, help="distinct samples kept in pinned host memory for e2e")
+    ap.add_argument("--cpu-samples", type=int, default=2, help="samples the cpu_baseline leg parses")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ workload
+class Workload(object):
+    """The rank's batch: synthetic pileups resident in HBM + each sample's variant-site list."""
+
+    def __init__(self, ctx, torch, args, rank):
+        from snp_pipeline_b200 import _lib
+        self.ctx, self.torch, self.args, self.rank = ctx, torch, args, rank
+        self.lib = _lib
+        self.n = args.samples
+        self.texts, self.nbytes, self.site_pos = [], [], []
+        cap = args.genome_len * 112 + 4096
+        scratch = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        for i in range(self.n):
+            spec = self.spec(i)
+            nb = ctx.synth_pileup_dev(spec, CONTIG, scratch.data_ptr(), cap)
+            t = torch.empty(nb + 64, dtype=torch.uint8, device="cuda")
+            t[:nb].copy_(scratch[:nb])
+            self.texts.append(t)
+            self.nbytes.append(nb)
+            self.site_pos.append(ctx.synth_sample_sites(spec))
+        del scratch
+        self.total_text = int(sum(self.nbytes))
+        keys = np.concatenate([p.astype(np.uint64) for p in self.site_pos])          # chrom rank 0
+        samp = np.concatenate([np.full(p.size, i, dtype=np.uint32) for i, p in enumerate(self.site_pos)])
+        self.keys_host, self.samp_host = keys, samp
+        self.keys_dev = torch.from_numpy(keys.view(np.int64)).cuda()
+        self.samp_dev = torch.from_numpy(samp.view(np.int32)).cuda()
+        nk = keys.size
+        self.uniq_dev = torch.empty(max(nk, 1), dtype=torch.int64, device="cuda")
+        self.cnt_dev = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
+        self.sout_dev = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
+        self.lines_dev = torch.empty(args.genome_len + 64, dtype=torch.int16, device="cuda")
+        self.stats_dev = torch.zeros((self.n, 5), dtype=torch.int64, device="cuda")
+        self.params = _lib.make_params(min_cons_depth=3)
+
+    def spec(self, i):
+        a = self.args
+        return self.lib.SynthSpec(SEED, self.rank * self.n + i, a.genome_len, 24, a.pool_sites, a.carry, 0.0)
+
+
+def build_sites(ctx, positions):
+    """Site table from the merged positions (one contig): snpgpu_sites_create via the array fast path."""
+    from snp_pipeline_b200 import _lib
+    return _lib.Sites.from_arrays(ctx, [CONTIG], np.zeros(positions.size, dtype=np.int32),
+                                  positions.astype(np.int64))
+
+
+def device_step(w, dist, world):
+    """One device-resident pass.  Returns (n_sites, matrix tensor, distance tensor)."""
+    torch, ctx = w.torch, w.ctx
+    nk = w.keys_host.size
+    n_uniq = ctx.merge_sites_dev(w.keys_dev.data_ptr(), w.samp_dev.data_ptr(), nk, w.uniq_dev.data_ptr(),
+                                 w.cnt_dev.data_ptr(), w.sout_dev.data_ptr())
+    local = w.uniq_dev[:n_uniq]
+    if world > 1:
+        # the path's one exchange step: all-gather of the per-rank sorted-unique site lists (NCCL over NVLink)
+        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        mine = torch.tensor([n_uniq], dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(counts, mine)
+        counts_h = counts.cpu().numpy()
+        mx = int(counts_h.max())
+        padded = torch.full((mx,), -1, dtype=torch.int64, device="cuda")
+        padded[:n_uniq] = local
+        gathered = torch.empty(world * mx, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered, padded)
+        parts = [gathered[r * mx: r * mx + int(counts_h[r])] for r in range(world)]
+        allkeys = torch.cat(parts)
+        owner = torch.cat([torch.full((int(counts_h[r]),), r, dtype=torch.int32, device="cuda") for r in range(world)])
+        gu = torch.empty_like(allkeys); gc = torch.empty(allkeys.numel(), dtype=torch.int32, device="cuda")
+        gs = torch.empty(allkeys.numel(), dtype=torch.int32, device="cuda")
+        n_uniq = ctx.merge_sites_dev(allkeys.data_ptr(), owner.data_ptr(), allkeys.numel(), gu.data_ptr(),
+                                     gc.data_ptr(), gs.data_ptr())
+        local = gu[:n_uniq]
+    positions = local.cpu().numpy()
+    sites = build_sites(ctx, positions)
+    matrix = torch.empty((w.n, max(n_uniq, 1)), dtype=torch.uint8, device="cuda")
+    for i in range(w.n):
+        ctx.pileup_consensus_dev(w.texts[i].data_ptr(), w.nbytes[i], sites, w.params, w.lib.MODE_ALL,
+                                 matrix[i].data_ptr(), w.lines_dev.data_ptr(), w.args.genome_len + 64,
+                                 w.stats_dev[i].data_ptr())
+    if world > 1:
+        full = torch.empty((world * w.n, matrix.shape[1]), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(full, matrix)
+    else:
+        full = matrix
+    lo = w.rank * w.n
+    d = torch.empty((w.n, full.shape[0]), dtype=torch.int32, device="cuda")
+    ctx.pairwise_distance_dev(full.data_ptr(), full.shape[0], n_uniq, full.shape[1], lo, lo + w.n, d.data_ptr())
+    sites.close()
+    return n_uniq, matrix, d
+
+
+def host_step(w, pool, pool_n, bufs):
+    """One end-to-end pass through the host-buffer C-ABI calls (what a ctypes user of the library makes)."""
+    ctx, lib = w.ctx, w.lib
+    uniq, cnt, samples = ctx.merge_sites(w.keys_host, w.samp_host)
+    sites = build_sites(ctx, uniq)
+    n_sites = uniq.size
+    rows, lines, stats = bufs
+    h2d = w.keys_host.nbytes + w.samp_host.nbytes
+    d2h = uniq.nbytes + cnt.nbytes + samples.nbytes
+    for i in range(w.n):
+        k = i % len(pool)
+        rc = ctx.lib.snpgpu_pileup_consensus(ctx.handle, ctypes.c_void_p(pool[k].ctypes.data), pool_n[k], sites.handle,
+                                             ctypes.byref(w.params), lib.MODE_ALL, ctypes.c_void_p(rows[i].ctypes.data),
+                                             ctypes.c_void_p(lines.ctypes.data), lines.size, ctypes.byref(stats))
+        ctx._check(rc)
+        h2d += pool_n[k]
+        d2h += n_sites + 2 * stats.n_lines + ctypes.sizeof(stats)
+    m = rows[:, :n_sites]
+    d = np.zeros((w.n, w.n), dtype=np.int32)
+    ctx._check(ctx.lib.snpgpu_pairwise_distance(ctx.handle, ctypes.c_void_p(rows.ctypes.data), w.n, n_sites,
+                                                rows.shape[1], ctypes.c_void_p(d.ctypes.data)))
+    h2d += w.n * rows.shape[1]
+    d2h += d.nbytes
+    sites.close()
+    return m, d, h2d, d2h
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_k1(orc, text, snps):
+    return orc.pileup_consensus(text, snps, [], orc.make_params(min_cons_depth=3), parse_all=True, want_lines=True)
+
+
+def cpu_baseline(w, matrix_host, n_samples):
+    """The oracle (CPU port of the reference's algorithm), one core, on a bounded sample of the same workload."""
+    from oracle import oracle as orc
+    orc.build()
+    uniq_t0 = time.perf_counter()
+    uniq, cnt, samples = orc.merge_sites_keys(w.keys_host, w.samp_host)
+    t_k2 = time.perf_counter() - uniq_t0
+    snps = [(CONTIG, int(p)) for p in uniq]
+    t_k1 = 0.0
+    for i in range(n_samples):
+        text = w.texts[i][:w.nbytes[i]].cpu().numpy()
+        t0 = time.perf_counter()
+        row, _ = cpu_k1(orc, text, snps)
+        t_k1 += time.perf_counter() - t0
+        assert row == matrix_host[i].tobytes(), "cpu_baseline: the oracle's row differs from the GPU's"
+    t0 = time.perf_counter()
+    d = orc.distance_matrix([bytes(r) for r in matrix_host])
+    t_k4 = time.perf_counter() - t0
+    t_step = t_k1 / n_samples * w.n + t_k2 + t_k4
+    return {"value": w.n * w.args.genome_len / t_step, "unit": "positions/s", "cores": 1, "kind": "port",
+            "sample": "%d of %d samples through the oracle's K1 (all-positions mode, %.1f s) scaled x%g, plus K2 "
+                      "(%.3f s) and K4 (%.2f s) on the full batch" % (n_samples, w.n, t_k1, w.n / n_samples, t_k2, t_k4),
+            "k1_positions_per_s_per_core": n_samples * w.args.genome_len / t_k1}, d
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference's path with every host thread, bounded sample."""
+    if rank != 0:
+        return
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    from snp_pipeline_b200 import _lib
+    orc.build()
+    orc.lib()
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    n_ref = max(1, min(cores, 16, args.samples))
+    ctx = _lib.Context(0)
+    cap = args.genome_len * 112 + 4096
+    scratch = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    texts, site_pos = [], []
+    for i in range(n_ref):
+        spec = _lib.SynthSpec(SEED, i, args.genome_len, 24, args.pool_sites, args.carry, 0.0)
+        nb = ctx.synth_pileup_dev(spec, CONTIG, scratch.data_ptr(), cap)
+        texts.append(scratch[:nb].cpu().numpy().copy())
+        site_pos.append(ctx.synth_sample_sites(spec))
+    del scratch
+    ctx.close()
+    keys = np.concatenate([p.astype(np.uint64) for p in site_pos])
+    samp = np.concatenate([np.full(p.size, i, dtype=np.uint32) for i, p in enumerate(site_pos)])
+
+    def step():
+        uniq, cnt, samples = orc.merge_sites_keys(keys, samp)
+        snps = [(CONTIG, int(p)) for p in uniq]
+        with ThreadPoolExecutor(max_workers=min(cores, n_ref)) as ex:     # ctypes drops the GIL inside the C call
+            rows = list(ex.map(lambda t: cpu_k1(orc, t, snps)[0], texts))
+        orc.distance_matrix(rows)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_ref * args.genome_len / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "positions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "positions/s", "cores": min(cores, n_ref), "kind": "port",
+                         "sample": "%d of %d samples per step, one thread each (oracle/snp_oracle.c, all-positions "
+                                   "mode) + K2 and K4 on those samples" % (n_ref, args.samples)},
+        "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[1]: synthetic %d samples x %.1f Mbp per GPU, ~%dk-site pool, depth ~24; "
+                        "call_consensus in all-positions mode (every line parsed)" %
+                        (args.samples, args.genome_len / 1e6, args.pool_sites // 1000),
+            "samples_per_gpu": args.samples, "genome_len": args.genome_len, "pool_sites": args.pool_sites,
+            "l2": "inputs (%.1f GB of text per GPU) exceed L2; no flush needed" % (args.samples * args.genome_len * 89e-9),
+            "host_pool_samples": args.host_pool, "parallelism": "samples sharded x%d" % world}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from snp_pipeline_b200 import _lib
+    ctx = _lib.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    w = Workload(ctx, torch, args, rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident: value ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        n_sites, matrix, d = device_step(w, dist, world)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.enable_timing(True)
+    ctx.kernel_time(0); ctx.kernel_time(1)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        n_sites, matrix, d = device_step(w, dist, world)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    k1_ms, k1_n = ctx.kernel_time(0)
+    k4_ms, k4_n = ctx.kernel_time(1)
+    ctx.enable_timing(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    positions = world * w.n * args.genome_len
+    value = positions / (ms_step * 1e-3)
+    stats = w.stats_dev.cpu().numpy()
+    assert (stats[:, 0] == args.genome_len).all() and (stats[:, 4] == 0).all(), "K1 reported an error"
+    matrix_host = matrix[:, :n_sites].cpu().numpy()
+    d_host = d.cpu().numpy()
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = (w.total_text + 2 * w.n * args.genome_len + w.n * n_sites) / w.n      # per launch: text + 2 B/line + row
+    k1_avg_ms = k1_ms / max(k1_n, 1)
+    achieved = alg_bytes / (k1_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "k1_pileup_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650",
+                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n,
+                "share_of_step": k1_ms / ms if ms else None,
+                "k4": {"avg_launch_ms": k4_ms / max(k4_n, 1), "pair_sites_per_s":
+                       (w.n * (world * w.n) * n_sites) / (k4_ms / max(k4_n, 1) * 1e-3) if k4_ms else None}}
+
+    # ---- end to end through the host-buffer C ABI ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ctx.set_stream(None)
+        pool, pool_n, owners = [], [], []
+        for k in range(min(args.host_pool, w.n)):
+            arr, owner = ctx.pinned_array(w.nbytes[k])
+            arr[:] = w.texts[k][:w.nbytes[k]].cpu().numpy()
+            pool.append(arr); pool_n.append(w.nbytes[k]); owners.append(owner)
+        rows_arr, rows_owner = ctx.pinned_array(w.n * ((n_sites + 63) // 64 * 64 + 64))
+        rows = rows_arr.reshape(w.n, -1)
+        lines_arr, lines_owner = ctx.pinned_array(2 * (args.genome_len + 64))
+        bufs = (rows, lines_arr.view(np.uint16), _lib.PileupStats())
+        for _ in range(max(1, min(args.warmup, 1))):
+            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item()) / e2e_steps
+        for k in range(w.n):
+            assert m[k].tobytes() == matrix_host[k % len(pool)].tobytes(), "e2e row differs from the device-resident row"
+        e2e = {"value": positions / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "h2d_gbs": h2d / e2e_s / 1e9}
+        for o in owners + [rows_owner, lines_owner]:
+            o.free()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, d_cpu = cpu_baseline(w, matrix_host, min(args.cpu_samples, w.n))
+        assert np.array_equal(d_cpu, d_host), "cpu_baseline: the oracle's distance matrix differs from the GPU's"
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "n_sites": int(n_sites), "matrix_cells_per_s": world * w.n * n_sites / (ms_step * 1e-3),
+            "text_gb_per_gpu": w.total_text / 1e9,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,14 @@ int         snpgpu_host_free(snpgpu_ctx *ctx, void *p);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t    snpgpu_launch_count(const snpgpu_ctx *ctx);
 
+/* Per-kernel device timing (bench.py's roofline): when enabled, every launch of the named kernel is bracketed by
+ * CUDA events on the context's stream.  snpgpu_kernel_time synchronises the stream, returns the summed device time
+ * and the number of launches since the last call, and resets both. */
+#define SNPGPU_KERNEL_PILEUP   0   /* k1_pileup_kernel   */
+#define SNPGPU_KERNEL_DISTANCE 1   /* k4_pairs_kernel (+ its pack kernel) */
+int         snpgpu_enable_timing(snpgpu_ctx *ctx, int on);
+int         snpgpu_kernel_time(snpgpu_ctx *ctx, int kernel, double *ms_out, uint64_t *launches_out);
+
 /* ---- consensus-caller parameters: ConsensusCaller.__init__ (pileup.py:433-471) + Reader's
  *      min_base_quality (pileup.py:389-407) -------------------------------------------------------- */
 typedef struct {

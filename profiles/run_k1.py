@@ -1,0 +1,32 @@
+"""Profiling driver: one synthetic 5 Mbp sample resident in HBM, K1 (all-positions mode) launched a few times.
+Usage (on the GPU box):  ncu --set full --clock-control none --import-source on -k regex:k1_pileup -s 2 -c 1 \
+                             -o gpurun_out/k1 python profiles/run_k1.py [sites|all] [n_launches]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from snp_pipeline_b200 import _lib
+
+mode = _lib.MODE_SITES if len(sys.argv) > 1 and sys.argv[1] == "sites" else _lib.MODE_ALL
+n_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+G = int(os.environ.get("GENOME_LEN", "5000000"))
+ctx = _lib.Context(0)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+spec = _lib.SynthSpec(20261017, 0, G, 24, G // 100, 0.05, 0.0)
+cap = G * 112 + 4096
+buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+n = ctx.synth_pileup_dev(spec, "gi|0000000|ref|SYN_5000K.1|", buf.data_ptr(), cap)
+pos = ctx.synth_sample_sites(spec)
+sites = _lib.Sites.from_arrays(ctx, ["gi|0000000|ref|SYN_5000K.1|"], np.zeros(pos.size, np.int32), pos.astype(np.int64))
+row = torch.empty(max(pos.size, 1), dtype=torch.uint8, device="cuda")
+lines = torch.empty(G + 64, dtype=torch.int16, device="cuda")
+stats = torch.zeros(5, dtype=torch.int64, device="cuda")
+p = _lib.make_params(min_cons_depth=3)
+ctx.enable_timing(True)
+for _ in range(n_launch):
+    ctx.pileup_consensus_dev(buf.data_ptr(), n, sites, p, mode, row.data_ptr(), lines.data_ptr(), G + 64, stats.data_ptr())
+torch.cuda.synchronize()
+ms, k = ctx.kernel_time(0)
+print("text bytes %d, K1 avg %.3f ms over %d launches -> %.1f GB/s; stats %s" % (n, ms / k, k, n / (ms / k) / 1e6, stats.tolist()))

@@ -20,7 +20,8 @@ FAIL_RAWDPTH, FAIL_VARFREQ, FAIL_DEPTH, FAIL_STRDPTH, FAIL_STRBIAS, FAIL_REGION 
 
 EXPORTS = [
     "snpgpu_abi_version", "snpgpu_create", "snpgpu_destroy", "snpgpu_last_error", "snpgpu_set_stream",
-    "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_sites_create",
+    "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_enable_timing",
+    "snpgpu_kernel_time", "snpgpu_sites_create",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
     "snpgpu_normalize_newlines_dev",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
@@ -93,6 +94,10 @@ def load():
     L.snpgpu_host_free.argtypes = [vp, vp]
     L.snpgpu_launch_count.restype = u64
     L.snpgpu_launch_count.argtypes = [vp]
+    L.snpgpu_enable_timing.restype = ctypes.c_int
+    L.snpgpu_enable_timing.argtypes = [vp, ctypes.c_int]
+    L.snpgpu_kernel_time.restype = ctypes.c_int
+    L.snpgpu_kernel_time.argtypes = [vp, ctypes.c_int, P(ctypes.c_double), P(u64)]
     L.snpgpu_sites_create.restype = ctypes.c_int
     L.snpgpu_sites_create.argtypes = [vp, ctypes.c_char_p, vp, i32, vp, vp, sz, vp, vp, sz, P(vp)]
     L.snpgpu_sites_destroy.restype = None
@@ -150,6 +155,29 @@ class Sites(object):
         ctx._check(rc)
         self.handle = h
 
+    @classmethod
+    def from_arrays(cls, ctx, contigs, snp_contig, snp_pos, exc_contig=None, exc_pos=None):
+        """Array fast path: contigs = list of names; snp_contig int32 indices into it, snp_pos int64."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.contigs = list(contigs)
+        enc = [n.encode("utf-8") for n in self.contigs]
+        blob = b"".join(enc)
+        off = np.zeros(len(enc) + 1, dtype=np.int32)
+        if enc:
+            off[1:] = np.cumsum([len(n) for n in enc])
+        sc = np.ascontiguousarray(snp_contig, dtype=np.int32)
+        sp = np.ascontiguousarray(snp_pos, dtype=np.int64)
+        ec = np.ascontiguousarray(exc_contig if exc_contig is not None else [], dtype=np.int32)
+        ep = np.ascontiguousarray(exc_pos if exc_pos is not None else [], dtype=np.int64)
+        self.n_snp = int(sp.size)
+        h = ctypes.c_void_p()
+        rc = ctx.lib.snpgpu_sites_create(ctx.handle, blob, _np_ptr(off), len(enc), _np_ptr(sc), _np_ptr(sp), sp.size,
+                                         _np_ptr(ec), _np_ptr(ep), ep.size, ctypes.byref(h))
+        ctx._check(rc)
+        self.handle = h
+        return self
+
     def close(self):
         if self.handle:
             self.ctx.lib.snpgpu_sites_destroy(self.handle)
@@ -203,6 +231,15 @@ class Context(object):
     @property
     def launch_count(self):
         return int(self.lib.snpgpu_launch_count(self.handle))
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.snpgpu_enable_timing(self.handle, 1 if on else 0))
+
+    def kernel_time(self, kernel):
+        """(summed device ms, launches) of kernel 0 = pileup, 1 = distance since the last call; synchronises."""
+        ms, n = ctypes.c_double(0), ctypes.c_uint64(0)
+        self._check(self.lib.snpgpu_kernel_time(self.handle, int(kernel), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
 
     def pinned_array(self, nbytes):
         """(uint8 ndarray over page-locked host memory, owner); call owner.free() when done with the array."""

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 using namespace snpgpu;
@@ -44,7 +45,28 @@ struct snpgpu_ctx {
     DevBuf k4_tmp, k4_mat, k4_dist;
     DevBuf synth_tmp, synth_n;
     size_t arena_want = 1 << 20;
+    bool   timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];     // pending event pairs per kernel id
+    std::vector<cudaEvent_t> spare_events;
 };
+
+namespace {
+struct TimedLaunch {       // brackets one launch with events when timing is on
+    snpgpu_ctx *ctx; int kernel; cudaEvent_t a = nullptr, b = nullptr;
+    cudaEvent_t get() {
+        if (!ctx->spare_events.empty()) { cudaEvent_t e = ctx->spare_events.back(); ctx->spare_events.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    TimedLaunch(snpgpu_ctx *c, int k) : ctx(c), kernel(k) {
+        if (ctx->timing) { a = get(); b = get(); cudaEventRecord(a, ctx->stream); }
+    }
+    ~TimedLaunch() {
+        if (a) { cudaEventRecord(b, ctx->stream); ctx->timed[kernel].push_back({a, b}); }
+    }
+};
+}  // namespace
 
 struct snpgpu_sites {
     snpgpu_ctx *ctx = nullptr;
@@ -104,6 +126,9 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
                      &ctx->synth_tmp, &ctx->synth_n};
     for (DevBuf *b : all) b->release();
+    for (int k = 0; k < 2; k++)
+        for (auto &pr : ctx->timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : ctx->spare_events) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -137,6 +162,30 @@ int snpgpu_host_free(snpgpu_ctx *ctx, void *p) {
 }
 
 uint64_t snpgpu_launch_count(const snpgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int snpgpu_enable_timing(snpgpu_ctx *ctx, int on) {
+    if (!ctx) return SNPGPU_E_ARG;
+    ctx->timing = on != 0;
+    return SNPGPU_OK;
+}
+
+int snpgpu_kernel_time(snpgpu_ctx *ctx, int kernel, double *ms_out, uint64_t *launches_out) {
+    if (!ctx || kernel < 0 || kernel > 1 || !ms_out || !launches_out) return fail(ctx, SNPGPU_E_ARG, "kernel_time: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    for (auto &pr : ctx->timed[kernel]) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        ctx->spare_events.push_back(pr.first);
+        ctx->spare_events.push_back(pr.second);
+    }
+    *ms_out = total;
+    *launches_out = ctx->timed[kernel].size();
+    ctx->timed[kernel].clear();
+    return SNPGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------------ site table
 int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t *name_off, int32_t n_contigs,
@@ -245,7 +294,10 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     a.arena = (uint8_t *)ctx->arena.p;
     a.arena_cap = ctx->arena.cap;
     const int bps = ctx->k1_blocks[params->min_base_qual > 0 ? 1 : 0];
-    ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
+    {
+        TimedLaunch t(ctx, SNPGPU_KERNEL_PILEUP);
+        ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
+    }
     if (sites->n_snp)
         ctx->launches += (uint64_t)k1_launch_row(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev);
     if (want_lines)
@@ -368,8 +420,12 @@ int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, siz
     CK(cudaSetDevice(ctx->device));
     CK(ctx->k4_tmp.ensure(k4_workspace_bytes(n_rows, n_sites)));
     int launches = 0;
-    int rc = k4_launch(ctx->stream, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, dist_out_dev,
+    int rc;
+    {
+        TimedLaunch t(ctx, SNPGPU_KERNEL_DISTANCE);
+        rc = k4_launch(ctx->stream, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, dist_out_dev,
                        ctx->k4_tmp.p, &launches);
+    }
     if (rc) return fail(ctx, rc, "pairwise_distance: launch failed");
     ctx->launches += (uint64_t)launches;
     return SNPGPU_OK;

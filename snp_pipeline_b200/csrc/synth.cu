@@ -11,7 +11,6 @@
 // read; one indel token on 0.1 % of the lines; zero-depth lines at 0.08 %; qualities Phred 13..39.
 #include "internal.h"
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
 #include <string.h>
 
 namespace snpgpu {
@@ -56,7 +55,7 @@ SNP_HD bool synth_carries(const SynthArgs &a, uint32_t pos) {
 template <bool WRITE>
 SNP_HD uint32_t synth_line(const SynthArgs &a, uint32_t pos, uint8_t *out) {
     uint32_t n = 0;
-#define PUT(ch) do { if (WRITE) out[n] = (uint8_t)(ch); n++; } while (0)
+#define PUT(ch) do { const uint8_t put_ch_ = (uint8_t)(ch); if (WRITE) out[n] = put_ch_; n++; } while (0)
     for (int i = 0; i < a.name_len; i++) PUT(a.name[i]);
     PUT('\t');
     char dig[12];
@@ -128,7 +127,7 @@ SNP_HD uint32_t synth_line(const SynthArgs &a, uint32_t pos, uint8_t *out) {
     return n;
 }
 
-__global__ void synth_len_kernel(const SynthArgs a, uint32_t *len) {
+__global__ void synth_len_kernel(const SynthArgs a, unsigned long long *len) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.genome_len) return;
     len[i] = synth_line<false>(a, i + 1u, nullptr);
@@ -146,15 +145,11 @@ __global__ void synth_write_kernel(const SynthArgs a, const unsigned long long *
     for (uint32_t k = 0; k < n; k++) text[o + k] = line[k];
 }
 
-struct LenToU64 {
-    __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
-};
-
 size_t synth_workspace_bytes(uint32_t genome_len) {
     size_t scan = 0;
-    cub::TransformInputIterator<unsigned long long, LenToU64, const uint32_t *> it((const uint32_t *)nullptr, LenToU64());
-    cub::DeviceScan::ExclusiveSum(nullptr, scan, it, (unsigned long long *)nullptr, (int)genome_len);
-    return ((size_t)genome_len * 4 + 255) / 256 * 256 + ((size_t)genome_len * 8 + 255) / 256 * 256 + scan + 512;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                  (int)genome_len);
+    return 2 * (((size_t)genome_len * 8 + 255) / 256 * 256) + scan + 512;
 }
 
 static SynthArgs make_args(const snpgpu_synth_spec &spec, const char *contig_name) {
@@ -183,16 +178,17 @@ int synth_launch(cudaStream_t stream, const snpgpu_synth_spec &spec, const char 
     if (spec.genome_len == 0) return SNPGPU_E_ARG;
     SynthArgs a = make_args(spec, contig_name);
     uint8_t *t = reinterpret_cast<uint8_t *>(tmp);
-    uint32_t *len = reinterpret_cast<uint32_t *>(t);
-    size_t o1 = ((size_t)spec.genome_len * 4 + 255) / 256 * 256;
+    unsigned long long *len = reinterpret_cast<unsigned long long *>(t);
+    size_t o1 = ((size_t)spec.genome_len * 8 + 255) / 256 * 256;
     unsigned long long *off = reinterpret_cast<unsigned long long *>(t + o1);
-    size_t o2 = o1 + ((size_t)spec.genome_len * 8 + 255) / 256 * 256;
+    size_t o2 = 2 * o1;
+    if (tmp_bytes < o2 + 256) return SNPGPU_E_NOMEM;
     size_t scan_bytes = tmp_bytes - o2;
     unsigned grid = (spec.genome_len + 127u) / 128u;
     synth_len_kernel<<<grid, 128, 0, stream>>>(a, len);
-    cub::TransformInputIterator<unsigned long long, LenToU64, const uint32_t *> it(len, LenToU64());
-    if (cub::DeviceScan::ExclusiveSum(t + o2, scan_bytes, it, off, (int)spec.genome_len, stream) != cudaSuccess)
-        return SNPGPU_E_CUDA;
+    cudaError_t se = cub::DeviceScan::ExclusiveSum(t + o2, scan_bytes, (const unsigned long long *)len, off,
+                                                   (int)spec.genome_len, stream);
+    if (se != cudaSuccess) return SNPGPU_E_CUDA;
     synth_write_kernel<<<grid, 128, 0, stream>>>(a, off, text_dev, cap, nbytes_dev);
     *launches += 4;
     return cudaGetLastError() == cudaSuccess ? 0 : SNPGPU_E_CUDA;
