@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_pileup_kernel(const PileupAr
                 const uint32_t s = sm.wstarts[w][k];
                 uint32_t e;
                 if (k + 1u < sm.pass_count[w]) e = (uint32_t)sm.wstarts[w][k + 1] - 1u;
+                else if (pass == 0u && k + 1u == sm.wcount[w] && w + 1 < K1_WARPS && sm.wcount[w + 1] > 0u)
+                    e = (uint32_t)sm.wstarts[w + 1][0] - 1u;            // the next region's first line follows
                 else e = find_nl(sm.buf, s, wlen);
                 const unsigned long long goff = base + s;
                 if (high || (e == wlen && base + wlen != a.nbytes)) {   // odd bytes, or the line leaves the window
