@@ -152,6 +152,7 @@ def build_sites(ctx, positions):
 
 def device_step(w, dist, world):
     """One device-resident pass.  Returns (n_sites, matrix tensor, distance tensor)."""
+    from snp_pipeline_b200 import sharding
     torch, ctx = w.torch, w.ctx
     nk = w.keys_host.size
     n_uniq = ctx.merge_sites_dev(w.keys_dev.data_ptr(), w.samp_dev.data_ptr(), nk, w.uniq_dev.data_ptr(),
@@ -159,16 +160,8 @@ def device_step(w, dist, world):
     local = w.uniq_dev[:n_uniq]
     if world > 1:
         # the path's one exchange step: all-gather of the per-rank sorted-unique site lists (NCCL over NVLink)
-        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
-        mine = torch.tensor([n_uniq], dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(counts, mine)
-        counts_h = counts.cpu().numpy()
-        mx = int(counts_h.max())
-        padded = torch.full((mx,), -1, dtype=torch.int64, device="cuda")
-        padded[:n_uniq] = local
-        gathered = torch.empty(world * mx, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(gathered, padded)
-        parts = [gathered[r * mx: r * mx + int(counts_h[r])] for r in range(world)]
+        parts = sharding.allgather_varlen(local, dist, world)
+        counts_h = [int(p.numel()) for p in parts]
         allkeys = torch.cat(parts)
         owner = torch.cat([torch.full((int(counts_h[r]),), r, dtype=torch.int32, device="cuda") for r in range(world)])
         gu = torch.empty_like(allkeys); gc = torch.empty(allkeys.numel(), dtype=torch.int32, device="cuda")
@@ -183,11 +176,7 @@ def device_step(w, dist, world):
         ctx.pileup_consensus_dev(w.texts[i].data_ptr(), w.nbytes[i], sites, w.params, w.lib.MODE_ALL,
                                  matrix[i].data_ptr(), w.lines_dev.data_ptr(), w.args.genome_len + 64,
                                  w.stats_dev[i].data_ptr())
-    if world > 1:
-        full = torch.empty((world * w.n, matrix.shape[1]), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(full, matrix)
-    else:
-        full = matrix
+    full = sharding.allgather_rows(matrix, dist, world)
     lo = w.rank * w.n
     d = torch.empty((w.n, full.shape[0]), dtype=torch.int32, device="cuda")
     ctx.pairwise_distance_dev(full.data_ptr(), full.shape[0], n_uniq, full.shape[1], lo, lo + w.n, d.data_ptr())
