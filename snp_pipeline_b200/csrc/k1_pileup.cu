@@ -28,6 +28,10 @@ struct K1Smem {
     uint16_t wstarts[K1_WARPS][K1_WCAP];   // line starts (buffer offsets) per warp region, file order
     uint32_t genq[K1_GENQ];                // fallback lines: (tile line index << 16) | buffer offset
     uint32_t wcount[K1_WARPS];             // line starts per warp region (all of them, recorded or not)
+    uint32_t full_prefix[K1_WARPS + 1];    // exclusive prefix of wcount: tile-level index of a region's first line
+    uint32_t pass_count[K1_WARPS];         // starts recorded in the current pass
+    uint32_t pass_prefix[K1_WARPS + 1];
+    uint32_t max_wcount;
     uint32_t n_genq;
     uint32_t tile_high;                    // some byte >= 0x80 in the window, or a CR that is not followed by LF
     unsigned long long n_parsed, n_general, n_lines;
@@ -265,51 +269,48 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_pileup_kernel(const PileupAr
         if (hi_acc & 0x80808080u) sm.tile_high = 1u;          // every line of the tile takes the exact path
         __syncthreads();
         // ---- parse ----------------------------------------------------------------------------------
-        // every thread derives the per-region counts of this pass from wcount[] itself (no extra barrier)
-        uint32_t n_tile_lines = 0, max_wc = 0;
-#pragma unroll
-        for (int w = 0; w < K1_WARPS; w++) {
-            const uint32_t c = sm.wcount[w];
-            n_tile_lines += c;
-            max_wc = c > max_wc ? c : max_wc;
+        if (tid == 0) {
+            uint32_t run = 0, mx = 0;
+            for (int w = 0; w < K1_WARPS; w++) {
+                sm.full_prefix[w] = run;
+                run += sm.wcount[w];
+                mx = sm.wcount[w] > mx ? sm.wcount[w] : mx;
+            }
+            sm.full_prefix[K1_WARPS] = run;
+            sm.max_wcount = mx;
         }
+        __syncthreads();
+        const uint32_t n_tile_lines = sm.full_prefix[K1_WARPS];
         const bool high = sm.tile_high != 0u;
-        const uint32_t n_pass = (max_wc + K1_WCAP - 1u) / K1_WCAP;
+        const uint32_t n_pass = (sm.max_wcount + K1_WCAP - 1u) / K1_WCAP;
         for (uint32_t pass = 0; pass < n_pass; pass++) {
             if (pass > 0) {
-                __syncthreads();                              // everyone is done with the previous pass's lists
                 uint32_t dummy = 0, dummy2 = 0;
                 k1_scan_region(sm, warp, lane, tile, wlen, pass, dummy, dummy2);
-                __syncthreads();
             }
-            const uint32_t done_before = pass * K1_WCAP;
-            uint32_t n_pass_lines = 0;
-#pragma unroll
-            for (int w = 0; w < K1_WARPS; w++) {
-                const uint32_t c = sm.wcount[w];
-                const uint32_t rem = c > done_before ? c - done_before : 0u;
-                n_pass_lines += rem < (uint32_t)K1_WCAP ? rem : (uint32_t)K1_WCAP;
-            }
-            for (uint32_t l = (uint32_t)tid; l < n_pass_lines; l += K1_THREADS) {
-                // locate line l of this pass: region w, index k within the pass, tile-level index line_idx
-                int w = 0;
-                uint32_t k = l, line_idx = 0, pcw = 0;
-                {
-                    uint32_t acc = 0, full = 0;
-                    bool found = false;
-#pragma unroll
-                    for (int x = 0; x < K1_WARPS; x++) {
-                        const uint32_t c = sm.wcount[x];
-                        const uint32_t rem = c > done_before ? c - done_before : 0u;
-                        const uint32_t pc = rem < (uint32_t)K1_WCAP ? rem : (uint32_t)K1_WCAP;
-                        if (!found && l < acc + pc) { found = true; w = x; k = l - acc; line_idx = full + done_before + k; pcw = pc; }
-                        acc += pc;
-                        full += c;
-                    }
+            if (tid == 0) {
+                uint32_t run = 0;
+                for (int w = 0; w < K1_WARPS; w++) {
+                    const uint32_t done = pass * K1_WCAP;
+                    const uint32_t rem = sm.wcount[w] > done ? sm.wcount[w] - done : 0u;
+                    const uint32_t c = rem < (uint32_t)K1_WCAP ? rem : (uint32_t)K1_WCAP;
+                    sm.pass_count[w] = c;
+                    sm.pass_prefix[w] = run;
+                    run += c;
                 }
+                sm.pass_prefix[K1_WARPS] = run;
+            }
+            __syncthreads();
+            const uint32_t n_pass_lines = sm.pass_prefix[K1_WARPS];
+            for (uint32_t l = (uint32_t)tid; l < n_pass_lines; l += K1_THREADS) {
+                int w = 0;
+#pragma unroll
+                for (int x = 1; x < K1_WARPS; x++) w += (l >= sm.pass_prefix[x]) ? 1 : 0;
+                const uint32_t k = l - sm.pass_prefix[w];
+                const uint32_t line_idx = sm.full_prefix[w] + pass * K1_WCAP + k;
                 const uint32_t s = sm.wstarts[w][k];
                 uint32_t e;
-                if (k + 1u < pcw) e = (uint32_t)sm.wstarts[w][k + 1] - 1u;
+                if (k + 1u < sm.pass_count[w]) e = (uint32_t)sm.wstarts[w][k + 1] - 1u;
                 else if (pass == 0u && k + 1u == sm.wcount[w] && w + 1 < K1_WARPS && sm.wcount[w + 1] > 0u)
                     e = (uint32_t)sm.wstarts[w + 1][0] - 1u;            // the next region's first line follows
                 else e = find_nl(sm.buf, s, wlen);
@@ -328,22 +329,20 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_pileup_kernel(const PileupAr
                     else th.general(goff, line_idx);
                 }
             }
-            __syncthreads();                                  // parse done: the queue is complete
+            __syncthreads();
             const uint32_t nq = sm.n_genq < (uint32_t)K1_GENQ ? sm.n_genq : (uint32_t)K1_GENQ;
-            if (nq) {                                         // uniform; rare
-                for (uint32_t g = (uint32_t)tid; g < nq; g += K1_THREADS) {
-                    const uint32_t v = sm.genq[g];
-                    th.general(base + (v & 0xffffu), v >> 16);
-                }
-                __syncthreads();
-                if (tid == 0) sm.n_genq = 0;
+            for (uint32_t g = (uint32_t)tid; g < nq; g += K1_THREADS) {
+                const uint32_t v = sm.genq[g];
+                th.general(base + (v & 0xffffu), v >> 16);
             }
+            __syncthreads();
+            if (tid == 0) sm.n_genq = 0;
         }
         if (tid == 0) {
             if (a.tile_nlines) a.tile_nlines[tile] = n_tile_lines;
             sm.n_lines += n_tile_lines;
         }
-        if (n_pass == 0u) __syncthreads();                    // (otherwise the barrier after the last parse did it)
+        __syncthreads();                                      // everyone is done with buf before it is refilled
     }
     // ---- statistics -------------------------------------------------------------------------------
     uint32_t np = th.n_parsed, ng = th.n_general;
