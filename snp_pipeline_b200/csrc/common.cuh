@@ -21,15 +21,18 @@ struct PileupStatusDev {
     unsigned int       pad;
 };
 
-// Tile geometry of the pileup kernel.
-constexpr int K1_TILE     = 32768;             // bytes of text whose line starts one tile owns
-constexpr int K1_LOOK     = 2048;              // extra bytes staged so that the last owned line is complete
+// Tile geometry of the pileup kernel: every warp is its own pipeline.
+constexpr int K1_LANE_CHUNKS = 17;             // 16-byte chunks one lane scans for newlines ...
+constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... = 272 bytes = 68 words: quarter warps hit disjoint banks
+constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // 8704 bytes of text whose line starts one tile owns
+constexpr int K1_LOOK     = 1024;              // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_THREADS  = 256;
-constexpr int K1_WARPS    = K1_THREADS / 32;
-constexpr int K1_WREGION  = K1_TILE / K1_WARPS;      // bytes scanned for newlines by one warp
-constexpr int K1_WCAP     = 128;               // line starts a warp records per pass (more -> another pass)
-constexpr int K1_GENQ     = 128;               // fallback lines queued per pass before they run inline
+constexpr int K1_WARPS    = 5;                 // independent warps per CTA
+constexpr int K1_THREADS  = 32 * K1_WARPS;
+constexpr int K1_CTAS_PER_SM = 4;              // 20 warps x 10.6 KiB of shared memory per SM
+constexpr int K1_WCAP     = 256;               // line starts a warp lists per pass (more -> another pass)
+constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
+constexpr int K1_QCAP     = 64;                // per-warp queue slots (drained whenever 32 are filled)
 constexpr int K1_MAXLINES = K1_TILE / 8;       // all-positions mode: a line that parses has >= 8 bytes
 
 struct PileupArgs {
@@ -60,16 +63,19 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// waits with a short sleep between polls, so that a waiting warp leaves the issue slots to the others
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -80,6 +86,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// pull [src, src + bytes) into L2 ahead of the bulk copy that will want it (bytes a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 }  // namespace snpgpu

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <vector>
 #include "line_fast.cuh"
+#include "line_quick.cuh"
 #include "line_general.cuh"
 #include "sites_host.h"
 
@@ -16,7 +17,8 @@ using namespace snpgpu;
 
 extern "C" {
 
-// counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code
+// counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code,
+// [5] = lines decided by the first-tier parser
 int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, const int32_t *name_off,
                   int32_t n_contigs, const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp,
                   const int32_t *exc_contig, const int64_t *exc_pos, size_t n_exc, const CallParams *p, int all_positions,
@@ -36,8 +38,11 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
     // classic-Mac line ends: what snpgpu_normalize_newlines_dev does before the kernel is run again (api.cu)
     for (size_t i = 0; i < nbytes; i++)
         if (buf[i] == '\r' && buf[i + 1] != '\n') buf[i] = '\n';
-    uint64_t n_lines = 0, n_parsed = 0, n_general = 0;
+    uint64_t n_lines = 0, n_parsed = 0, n_general = 0, n_quick = 0;
     int hint = 0;
+    uint32_t cc_name[16];
+    ContigCache cc;
+    contig_cache_load(t, hint, cc_name, 16, &cc);
     size_t s = 0;
     counters[3] = ~0ull; counters[4] = 0;
     std::vector<uint8_t> scratch;
@@ -52,7 +57,17 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         const size_t line_idx = n_lines++;
         int st = ST_FALLBACK;
         FastLine fl;
-        if (!force_general && !high) {
+        if (!force_general && !high && p->min_base_qual <= 0) {       // first tier (line_quick.cuh)
+            QuickLine q;
+            if (cc.cid != hint) contig_cache_load(t, hint, cc_name, 16, &cc);    // the kernel reloads after a drain
+            st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
+            if (st == ST_OK) {
+                if (q.end != e) { counters[3] = s; counters[4] = 99; break; }   // harness self-check: the line end
+                fl.base = q.base; fl.fail = q.fail; fl.site = q.site;
+                n_quick++;
+            }
+        }
+        if (!force_general && !high && (st == ST_DETAIL || p->min_base_qual > 0)) {
             if (p->min_base_qual > 0) st = fast_line<true>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);
             else st = fast_line<false>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);
         }
@@ -106,7 +121,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         uint64_t c = cells[h.snp_unique[k]];
         row_out[k] = c ? (uint8_t)(c & 0xff) : (uint8_t)'-';
     }
-    counters[0] = n_lines; counters[1] = n_parsed; counters[2] = n_general;
+    counters[0] = n_lines; counters[1] = n_parsed; counters[2] = n_general; counters[5] = n_quick;
     return (int)counters[4];
 }
 

@@ -3,52 +3,45 @@
 // Replaces the per-sample hot loop of the reference (call_consensus.py:161-188): pileup.Reader.__iter__
 // (pileup.py:408-429), pileup.Record (pileup.py:209-325) and ConsensusCaller.call_consensus (pileup.py:492-590).
 //
-// Shape of the kernel:
-//   * persistent CTAs stride over 32 KiB tiles of the text; a tile owns the lines whose preceding '\n' lies
-//     inside it (the first line of the file belongs to tile 0);
-//   * each tile (+2 KiB of look-ahead so the last owned line is complete) is staged into shared memory by ONE
-//     1-D bulk async copy (TMA engine, mbarrier completion) -- no register staging, fully coalesced;
-//   * scan: every thread tests 16-byte chunks for '\n' with SWAR arithmetic, a ballot turns the hits of a warp
-//     into ordered line-start lists (and a tile-wide "byte >= 0x80 present" flag);
-//   * parse: one thread per line runs the fast parser (line_fast.cuh) out of shared memory, four bases per
-//     32-bit load; lines it declines are queued and run through the exact any-input parser
-//     (line_general.cuh) on the text in global memory afterwards, so the common path stays convergent;
+// Shape of the kernel: every WARP is its own pipeline -- no block-wide barrier anywhere.
+//   * a warp strides over 8.5 KiB tiles of the text; a tile owns the lines whose preceding '\n' lies inside it
+//     (the first line of the file belongs to tile 0);
+//   * the tile (+1 KiB of look-ahead so the last owned line is complete) is staged into the warp's slice of
+//     shared memory by ONE 1-D bulk async copy (TMA engine, mbarrier completion); the other resident warps
+//     compute while this one waits;
+//   * scan: lane L owns bytes [272 L, 272 L + 272) of the tile (a 68-word stride, so the 16-byte loads of a
+//     quarter warp fall into disjoint banks), tests them for '\n' with SWAR arithmetic and keeps the 17 hit
+//     masks in registers; ONE warp prefix sum over the per-lane counts then orders all line starts of the tile;
+//   * parse: one lane per line, 32 lines in lock step, through the first-tier parser (line_quick.cuh);
+//   * the few lines it declines are queued per warp (by file offset) and, whenever 32 have piled up, run densely
+//     through the exact-tally parser (line_fast.cuh) and, from there, the any-input parser (line_general.cuh),
+//     both on the text where it lies in global memory (an L2 hit);
 //   * results: an atomicMax per hit site keeps the LAST line of a position in file order (the dict overwrite
 //     of call_consensus.py:169-176); in all-positions mode a uint16 per line is staged per tile and compacted
 //     to file order by a second tiny kernel.
-// Algorithmic traffic: every text byte read once (+6 % look-ahead re-read, an L2 hit), 2 B written per line.
+// Algorithmic traffic: every text byte read once (+12 % look-ahead re-read, an L2 hit), 2 B written per line.
 #include "internal.h"
 #include "line_fast.cuh"
+#include "line_quick.cuh"
 #include "line_general.cuh"
 
 namespace snpgpu {
 
-struct K1Smem {
-    alignas(16) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
-    uint16_t wstarts[K1_WARPS][K1_WCAP];   // line starts (buffer offsets) per warp region, file order
-    uint32_t genq[K1_GENQ];                // fallback lines: (tile line index << 16) | buffer offset
-    uint32_t wcount[K1_WARPS];             // line starts per warp region (all of them, recorded or not)
-    uint32_t full_prefix[K1_WARPS + 1];    // exclusive prefix of wcount: tile-level index of a region's first line
-    uint32_t pass_count[K1_WARPS];         // starts recorded in the current pass
-    uint32_t pass_prefix[K1_WARPS + 1];
-    uint32_t max_wcount;
-    uint32_t n_genq;
-    uint32_t tile_high;                    // some byte >= 0x80 in the window, or a CR that is not followed by LF
-    unsigned long long n_parsed, n_general, n_lines;
+struct K1Warp {                                 // one warp's slice of shared memory
+    alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
+    uint16_t starts[K1_WCAP];                   // line starts (buffer offsets) of the current pass, file order
+    uint32_t cname[K1_NAMEW];                   // name + tab of the contig the warp expects (ContigCache::name4)
+    unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh:  (line index in its tile << 48) | file offset
+    unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
     alignas(8) uint64_t bar;
 };
 
-size_t k1_smem_bytes() { return sizeof(K1Smem); }
+size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
 
 // exact per-byte mask (0x80 where the byte equals '\n'), any byte values
 __device__ __forceinline__ uint32_t nl_mask(uint32_t w) {
     uint32_t t = w ^ 0x0a0a0a0au;
     return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
-}
-
-// the same for words whose bytes are all < 0x80 (no carries between byte lanes): one operation less
-__device__ __forceinline__ uint32_t nl_mask7(uint32_t w) {
-    return ~((w ^ 0x0a0a0a0au) + 0x7f7f7f7fu) & 0x80808080u;
 }
 
 // non-zero in bit 7 of some byte iff the word holds a '\r' (plus borrow artefacts above one: only an "any" test)
@@ -75,291 +68,391 @@ __device__ __noinline__ bool lone_cr_in_chunk(const uint8_t *buf, uint32_t off) 
     return lone;
 }
 
-// first '\n' at or after buf[i], or limit
-__device__ __forceinline__ uint32_t find_nl(const uint8_t *buf, uint32_t i, uint32_t limit) {
-    while (i < limit) {
-        uint32_t t = load_u32(buf, i) ^ 0x0a0a0a0au;
-        uint32_t z = (t - 0x01010101u) & ~t & 0x80808080u;
-        if (z) {
-            uint32_t p = i + ((uint32_t)ctz32(z) >> 3);
-            return p < limit ? p : limit;
-        }
-        i += 4u;
-    }
-    return limit;
-}
-
-struct K1Thread {
-    const PileupArgs &a;
-    K1Smem &sm;
-    int tile;
-    unsigned long long base;
+// What the second and third tier keep between calls.  It lives in local memory (its address is passed to the
+// out-of-line tiers); the first tier never touches it.
+struct K1Cold {
+    int hint;                     // contig of this lane's previous second-tier line (line_fast.cuh moves it)
     uint32_t n_parsed, n_general;
-
-    __device__ __forceinline__ void report(unsigned long long goff, int code) {
-        atomicMin(&a.st->first_error, (goff << 8) | (unsigned long long)code);
-    }
-
-    // call_consensus.py:165-176: Region failure, '-' substitution, keep the cell for the snplist gather
-    __device__ __forceinline__ void emit(unsigned base_ch, unsigned fail, int32_t site, unsigned long long goff,
-                                         uint32_t line_idx) {
-        unsigned flags = site >= 0 ? a.sites.flags[site] : 0u;
-        if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
-        unsigned cell = (fail || base_ch == '*') ? (unsigned)'-' : base_ch;
-        if (flags & SITE_SNP) atomicMax(&a.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
-        if (a.line_stage && line_idx < (uint32_t)K1_MAXLINES)
-            a.line_stage[(size_t)tile * K1_MAXLINES + line_idx] = (uint16_t)(cell | (fail << 8));
-        n_parsed++;
-    }
-
-    // the exact path, on the text where it lies in global memory
-    __device__ __noinline__ void general(unsigned long long goff, uint32_t line_idx) {
-        const uint8_t *line = a.text + goff;
-        unsigned long long room = a.nbytes - goff;
-        int64_t n = 0;
-        bool lone_cr = false;
-        while ((unsigned long long)n < room && line[n] != '\n') {
-            if (line[n] == '\r' && (unsigned long long)(n + 1) < room && line[n + 1] != '\n') lone_cr = true;
-            n++;
-        }
-        n_general++;
-        if (lone_cr) { report(goff, ST_LONECR); return; }   // classic-Mac line end: the caller normalises and reruns
-        LineCall r;
-        const bool all = a.mode == SNPGPU_MODE_ALL;
-        int32_t site = -1;
-        if (!all) {
-            general_key(line, n, &r);                         // pileup.py:423-427
-            if (r.status) { report(goff, r.status); return; }
-            int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
-            site = site_find(a.sites, cid, r.pos);
-            if (site < 0) return;
-        }
-        general_line(line, n, a.p, nullptr, 0, &r);
-        if (r.status == ST_NEED_ARENA) {
-            unsigned long long want = ((unsigned long long)r.bases_len + 15ull) & ~15ull;
-            unsigned long long off = atomicAdd(&a.st->arena_used, want);
-            if (off + want > a.arena_cap) { atomicExch(&a.st->arena_overflow, 1u); return; }
-            general_line(line, n, a.p, a.arena + off, r.bases_len, &r);
-        }
-        if (r.status) { report(goff, r.status); return; }
-        if (all) {
-            int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
-            site = site_find(a.sites, cid, r.pos);
-        }
-        emit(r.base, r.fail, site, goff, line_idx);
-    }
 };
 
-// One pass of the newline scan over this warp's 4 KiB region.  Records the starts whose index within the
-// region falls in [pass * K1_WCAP, (pass + 1) * K1_WCAP); returns the region's total number of starts.
-__device__ __forceinline__ uint32_t k1_scan_region(K1Smem &sm, int warp, int lane, int tile, uint32_t wlen,
-                                                   uint32_t pass, uint32_t &hi_acc, uint32_t &cr_acc) {
-    uint32_t wtotal = 0;
-    const uint32_t lo_idx = pass * K1_WCAP;
-    if (tile == 0 && warp == 0 && wlen > 0) {                 // the first line of the file
-        if (lane == 0 && pass == 0) sm.wstarts[0][0] = 0;
-        wtotal = 1;
-    }
-    const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll 2
-    for (int it = 0; it < K1_WREGION / 512; it++) {
-        const uint32_t off = (uint32_t)warp * K1_WREGION + (uint32_t)it * 512u + (uint32_t)lane * 16u;
-        uint32_t m = 0;                                       // bit 8*b + w  <->  byte 4*w + b of the chunk
-        if (off < wlen) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
-            hi_acc |= v.x | v.y | v.z | v.w;
-            cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
-            if ((v.x | v.y | v.z | v.w) & 0x80808080u)         // exact form when a byte >= 0x80 is around
-                m = (nl_mask(v.x) >> 7) | (nl_mask(v.y) >> 6) | (nl_mask(v.z) >> 5) | (nl_mask(v.w) >> 4);
-            else
-                m = (nl_mask7(v.x) >> 7) | (nl_mask7(v.y) >> 6) | (nl_mask7(v.z) >> 5) | (nl_mask7(v.w) >> 4);
-            if (off + 17u > wlen) {                           // last chunk of the text: a start must be < wlen
-                for (uint32_t pos = 0; pos < 16u; pos++)
-                    if (off + pos + 1u >= wlen) m &= ~(1u << (8u * (pos & 3u) + (pos >> 2)));
-            }
-        }
-        const uint32_t cnt = (uint32_t)__popc(m);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, cnt > 0u);
-        const uint32_t b2 = __ballot_sync(0xffffffffu, cnt > 1u);
-        uint32_t excl, total;
-        if (b2 == 0u) {
-            excl = (uint32_t)__popc(b1 & lt_mask);
-            total = (uint32_t)__popc(b1);
-        } else {
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            excl = incl - cnt;
-            total = __shfl_sync(0xffffffffu, incl, 31);
-        }
-        uint32_t idx = wtotal + excl - lo_idx;                // wraps when below this pass: rejected by < K1_WCAP
-        if (cnt == 1u) {
-            const uint32_t f = (uint32_t)ctz32(m);
-            if (idx < (uint32_t)K1_WCAP) sm.wstarts[warp][idx] = (uint16_t)(off + (f & 7u) * 4u + (f >> 3) + 1u);
-        } else if (cnt > 1u) {
-            for (uint32_t pos = 0; pos < 16u; pos++) {
-                if ((m >> (8u * (pos & 3u) + (pos >> 2))) & 1u) {
-                    if (idx < (uint32_t)K1_WCAP) sm.wstarts[warp][idx] = (uint16_t)(off + pos + 1u);
-                    idx++;
-                }
-            }
-        }
-        wtotal += total;
-    }
-    return wtotal;
+__device__ __forceinline__ void k1_report(const PileupArgs &a, unsigned long long goff, int code) {
+    atomicMin(&a.st->first_error, (goff << 8) | (unsigned long long)code);
 }
 
-template <bool HAS_QUAL>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_pileup_kernel(const PileupArgs a) {
+// call_consensus.py:165-176: Region failure, '-' substitution, keep the cell for the snplist gather.
+// stage_idx: slot of the line in line_stage (tile * K1_MAXLINES + line index in the tile), ~0 for none.
+__device__ __forceinline__ void k1_emit(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                        unsigned long long goff, size_t stage_idx) {
+    unsigned flags = site >= 0 ? a.sites.flags[site] : 0u;
+    if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
+    unsigned cell = (fail || base_ch == '*') ? (unsigned)'-' : base_ch;
+    if (flags & SITE_SNP) atomicMax(&a.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
+    if (a.line_stage && stage_idx != ~(size_t)0) a.line_stage[stage_idx] = (uint16_t)(cell | (fail << 8));
+}
+
+// slot in line_stage of the line that starts at file offset goff and is the line_idx-th of its tile (the tile
+// holding the byte in front of it)
+__device__ __forceinline__ size_t k1_stage_idx(unsigned long long goff, uint32_t line_idx) {
+    if (line_idx >= (uint32_t)K1_MAXLINES) return ~(size_t)0;
+    const unsigned long long tile = goff ? (goff - 1ull) / (unsigned long long)K1_TILE : 0ull;
+    return (size_t)tile * K1_MAXLINES + line_idx;
+}
+
+// third tier: the exact any-input parser, on the text where it lies in global memory
+__device__ __noinline__ void k1_general(const PileupArgs &a, K1Cold &cs, unsigned long long goff, uint32_t line_idx) {
+    const uint8_t *line = a.text + goff;
+    unsigned long long room = a.nbytes - goff;
+    int64_t n = 0;
+    bool lone_cr = false;
+    while ((unsigned long long)n < room && line[n] != '\n') {
+        if (line[n] == '\r' && (unsigned long long)(n + 1) < room && line[n + 1] != '\n') lone_cr = true;
+        n++;
+    }
+    cs.n_general++;
+    if (lone_cr) { k1_report(a, goff, ST_LONECR); return; }   // classic-Mac line end: the caller normalises and reruns
+    LineCall r;
+    const bool all = a.mode == SNPGPU_MODE_ALL;
+    int32_t site = -1;
+    if (!all) {
+        general_key(line, n, &r);                             // pileup.py:423-427
+        if (r.status) { k1_report(a, goff, r.status); return; }
+        int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
+        site = site_find(a.sites, cid, r.pos);
+        if (site < 0) return;
+    }
+    general_line(line, n, a.p, nullptr, 0, &r);
+    if (r.status == ST_NEED_ARENA) {
+        unsigned long long want = ((unsigned long long)r.bases_len + 15ull) & ~15ull;
+        unsigned long long off = atomicAdd(&a.st->arena_used, want);
+        if (off + want > a.arena_cap) { atomicExch(&a.st->arena_overflow, 1u); return; }
+        general_line(line, n, a.p, a.arena + off, r.bases_len, &r);
+    }
+    if (r.status) { k1_report(a, goff, r.status); return; }
+    if (all) {
+        int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
+        site = site_find(a.sites, cid, r.pos);
+    }
+    k1_emit(a, r.base, r.fail, site, goff, k1_stage_idx(goff, line_idx));
+    cs.n_parsed++;
+}
+
+// second tier: exact tallies (line_fast.cuh) on the text in global memory; returns true when the line has to
+// go on to k1_general().  The words line_fast reads may reach 7 bytes past the line end, so the last lines of
+// the text are left to k1_general(), which reads byte by byte.
+template <bool HAS_QUAL, bool ALL>
+__device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned long long goff, uint32_t line_idx) {
+    const unsigned long long room = a.nbytes - goff;
+    const unsigned long long abase = goff & ~15ull;
+    const uint8_t *buf = a.text + abase;
+    const uint32_t s = (uint32_t)(goff - abase);
+    const uint32_t cap = room < 65536ull ? (uint32_t)room : 65536u;
+    uint32_t n = 0;
+    while (n < cap && buf[s + n] != '\n') n++;
+    if (n == cap || (unsigned long long)n + 8ull > room) return true;          // very long, or at the end of the text
+    FastLine fl;
+    const int st = fast_line<HAS_QUAL>(buf, s, s + n, a.sites, cs.hint, a.p, ALL, &fl);
+    if (st == ST_OK) {
+        k1_emit(a, fl.base, fl.fail, fl.site, goff, k1_stage_idx(goff, line_idx));
+        cs.n_parsed++;
+    }
+    return st == ST_FALLBACK;
+}
+
+// ---- the per-warp queues (all 32 lanes call these together; the fill counts are warp-uniform) -------------
+__device__ __forceinline__ uint32_t k1_push(unsigned long long *q, uint32_t n_q, int lane, bool want,
+                                            unsigned long long entry) {
+    const uint32_t b = __ballot_sync(0xffffffffu, want);
+    if (b == 0u) return n_q;
+    if (want) q[n_q + (uint32_t)__popc(b & ((1u << lane) - 1u))] = entry;
+    __syncwarp();
+    return n_q + (uint32_t)__popc(b);
+}
+
+// runs queued lines through k1_general(), 32 at a time, while at least 32 wait (all of them when flush)
+__device__ __noinline__ uint32_t k1_drain_general(const PileupArgs &a, K1Warp &sm, K1Cold &cs, int lane, uint32_t n_gq,
+                                                  bool flush) {
+    while (n_gq >= 32u || (flush && n_gq > 0u)) {
+        const uint32_t take = n_gq < 32u ? n_gq : 32u;
+        n_gq -= take;
+        unsigned long long e = 0;
+        const bool mine = (uint32_t)lane < take;
+        if (mine) e = sm.gq[n_gq + (uint32_t)lane];
+        __syncwarp();
+        if (mine) k1_general(a, cs, e & 0xffffffffffffull, (uint32_t)(e >> 48));
+        __syncwarp();
+    }
+    return n_gq;
+}
+
+// the same for k1_detail(); what it declines moves to the general queue.  Returns n_dq | n_gq << 16.
+template <bool HAS_QUAL, bool ALL>
+__device__ __noinline__ uint32_t k1_drain_detail(const PileupArgs &a, K1Warp &sm, K1Cold &cs, int lane, uint32_t n_dq,
+                                                 uint32_t n_gq, bool flush) {
+    while (n_dq >= 32u || (flush && n_dq > 0u)) {
+        const uint32_t take = n_dq < 32u ? n_dq : 32u;
+        n_dq -= take;
+        unsigned long long e = 0;
+        const bool mine = (uint32_t)lane < take;
+        if (mine) e = sm.dq[n_dq + (uint32_t)lane];
+        __syncwarp();
+        bool more = false;
+        if (mine) more = k1_detail<HAS_QUAL, ALL>(a, cs, e & 0xffffffffffffull, (uint32_t)(e >> 48));
+        __syncwarp();
+        n_gq = k1_push(sm.gq, n_gq, lane, more, e);
+        n_gq = k1_drain_general(a, sm, cs, lane, n_gq, false);
+    }
+    return n_dq | (n_gq << 16);
+}
+
+// A tile with a byte >= 0x80 or a lone CR in its window: every line goes to k1_general().  Byte-wise on purpose
+// (no SWAR assumption holds here).  Returns the number of lines the tile owns | n_gq << 16.
+__device__ __noinline__ uint32_t k1_slow_tile(const PileupArgs &a, K1Warp &sm, K1Cold &cs, int lane, uint32_t n_gq,
+                                              int tile, unsigned long long base, uint32_t wlen) {
+    const uint32_t lo = (uint32_t)lane * K1_LANE_BYTES;
+    uint32_t hi = lo + K1_LANE_BYTES;
+    if (hi > wlen) hi = wlen;
+    uint32_t cnt = 0;
+    for (uint32_t i = lo; i < hi; i++)
+        if (sm.buf[i] == '\n' && i + 1u < wlen) cnt++;
+    const bool first = tile == 0 && lane == 0 && wlen > 0;
+    if (first) cnt++;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t idx = incl - cnt, cur = lo;
+    bool pending_first = first;
+    while (__any_sync(0xffffffffu, cnt > 0u)) {
+        unsigned long long entry = 0;
+        const bool want = cnt > 0u;
+        if (want) {
+            uint32_t s = 0;
+            if (pending_first) pending_first = false;
+            else {
+                while (!(sm.buf[cur] == '\n' && cur + 1u < wlen)) cur++;
+                s = ++cur;
+            }
+            entry = ((unsigned long long)idx << 48) | (base + s);
+            idx++; cnt--;
+        }
+        n_gq = k1_push(sm.gq, n_gq, lane, want, entry);
+        n_gq = k1_drain_general(a, sm, cs, lane, n_gq, false);
+    }
+    return total | (n_gq << 16);
+}
+
+// newline flags of the 16 bytes at buf[off ..]: bit 8*b + w  <->  byte 4*w + b.  Needs every byte < 0x80.
+__device__ __forceinline__ uint32_t k1_chunk_mask(const uint4 v, uint32_t off, uint32_t wlen) {
+    const uint32_t NL = 0x0a0a0a0au, K = 0x7f7f7f7fu, H = 0x80808080u;
+    const uint32_t x0 = (v.x ^ NL) + K, x1 = (v.y ^ NL) + K, x2 = (v.z ^ NL) + K, x3 = (v.w ^ NL) + K;
+    uint32_t m = ((~x0 & H) >> 7) | ((~x1 & H) >> 6) | ((~x2 & H) >> 5) | ((~x3 & H) >> 4);
+    if (off + 17u > wlen) {                                   // last chunk of the text: a start must be < wlen
+#pragma unroll 1
+        for (uint32_t pos = wlen - 1u - off; pos < 16u; pos++) m &= ~(1u << (8u * (pos & 3u) + (pos >> 2)));
+    }
+    return m;
+}
+
+// appends the line starts flagged in m (chunk number `chunk`) to the pass's list as (chunk << 5 | flag bit)
+__device__ __forceinline__ void k1_list_hits(uint16_t *starts, uint32_t m, uint32_t chunk, uint32_t &idx) {
+    if (m == 0u) return;
+    const uint32_t chunk5 = chunk << 5;
+    if ((m & (m - 1u)) == 0u) {
+        if (idx < (uint32_t)K1_WCAP) starts[idx] = (uint16_t)(chunk5 | (uint32_t)ctz32(m));
+        idx++;
+    } else {                                                  // lines shorter than 16 bytes: in byte order
+#pragma unroll 1
+        for (uint32_t pos = 0; pos < 16u; pos++) {
+            const uint32_t f = 8u * (pos & 3u) + (pos >> 2);
+            if ((m >> f) & 1u) {
+                if (idx < (uint32_t)K1_WCAP) starts[idx] = (uint16_t)(chunk5 | f);
+                idx++;
+            }
+        }
+    }
+}
+
+// the list of a later pass (more than K1_WCAP lines in the tile: very short lines): scans the window again
+__device__ __noinline__ void k1_relist(K1Warp &sm, int lane, uint32_t wlen, uint32_t idx) {
+    for (int j = 0; j < K1_LANE_CHUNKS; j++) {
+        const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
+        if (off >= wlen) break;
+        const uint32_t m = k1_chunk_mask(*reinterpret_cast<const uint4 *>(sm.buf + off), off, wlen);
+        k1_list_hits(sm.starts, m, (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, idx);
+    }
+}
+
+// HAS_QUAL: a minimum base quality is set (call_consensus -q > 0): every line goes straight to line_fast.cuh,
+// which pairs each base with its quality.  ALL: all-positions mode (compile-time so that the scan can drop its
+// '\r' test: there the parsers look at every byte of every line themselves).
+template <bool HAS_QUAL, bool ALL>
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(const __grid_constant__ PileupArgs a) {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
-    K1Smem &sm = *reinterpret_cast<K1Smem *>(k1_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    K1Warp &sm = reinterpret_cast<K1Warp *>(k1_smem_raw)[warp];
+    if (lane == 0) {
         mbar_init(&sm.bar, 1);
         mbar_fence_init();
-        sm.n_parsed = 0; sm.n_general = 0; sm.n_lines = 0;
     }
-    __syncthreads();
-    uint32_t parity = 0;
-    int hint = 0;
-    K1Thread th{a, sm, 0, 0ull, 0u, 0u};
-    const bool all = a.mode == SNPGPU_MODE_ALL;
+    __syncwarp();
+    uint32_t parity = 0, n_dq = 0, n_gq = 0, n_parsed = 0;
+    unsigned long long n_lines = 0;
+    K1Cold cs{0, 0u, 0u};
+    constexpr bool CHECK_CR = !ALL || HAS_QUAL;
+    constexpr uint32_t H = 0x80808080u;
+    const int gwarp = blockIdx.x * K1_WARPS + warp, n_gwarps = gridDim.x * K1_WARPS;
+    ContigCache cc;
+    contig_cache_load(a.sites, 0, sm.cname, K1_NAMEW, &cc);   // every lane writes the same words
+    __syncwarp();
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tile = gwarp; tile < a.n_tiles; tile += n_gwarps) {
+        {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
+            const int hint = cs.hint;
+            const uint32_t moved = __ballot_sync(0xffffffffu, hint != cc.cid);
+            if (moved) {
+                const int nh = __shfl_sync(0xffffffffu, hint, 31 - __clz((int)moved));
+                cs.hint = nh;
+                __syncwarp();
+                contig_cache_load(a.sites, nh, sm.cname, K1_NAMEW, &cc);
+            }
+        }
         const unsigned long long base = (unsigned long long)tile * K1_TILE;
         const unsigned long long left = a.nbytes - base;
         const uint32_t wlen = left < (unsigned long long)(K1_TILE + K1_LOOK) ? (uint32_t)left : (uint32_t)(K1_TILE + K1_LOOK);
         const uint32_t bulk = wlen & ~15u;
-        th.tile = tile; th.base = base;
+        const bool eof = left <= (unsigned long long)(K1_TILE + K1_LOOK);
+        const size_t stage0 = (size_t)tile * K1_MAXLINES;
         // ---- stage the window ---------------------------------------------------------------------
-        if (tid == 0) {
-            sm.n_genq = 0; sm.tile_high = 0;
-            if (bulk) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&sm.bar, bulk);
-                bulk_g2s(sm.buf, a.text + base, bulk, &sm.bar);
+        __syncwarp();                                         // every lane is done with the previous window
+        if (lane == 0 && bulk) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&sm.bar, bulk);
+            bulk_g2s(sm.buf, a.text + base, bulk, &sm.bar);
+            const unsigned long long nbase = base + (unsigned long long)n_gwarps * K1_TILE;   // this warp's next tile -> L2
+            if (nbase < a.nbytes) {
+                const unsigned long long nleft = a.nbytes - nbase;
+                const uint32_t nb = (nleft < (unsigned long long)(K1_TILE + K1_LOOK) ? (uint32_t)nleft : (uint32_t)(K1_TILE + K1_LOOK)) & ~15u;
+                if (nb) bulk_prefetch_l2(a.text + nbase, nb);
             }
         }
-        for (uint32_t j = bulk + (uint32_t)tid; j < wlen + (uint32_t)K1_PAD; j += K1_THREADS)
+        for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         if (bulk) { mbar_wait(&sm.bar, parity); parity ^= 1u; }
-        __syncthreads();
-        // ---- scan: line starts + high-bit flag ----------------------------------------------------
-        uint32_t hi_acc = 0, cr_acc = 0;
-        uint32_t wtotal = k1_scan_region(sm, warp, lane, tile, wlen, 0u, hi_acc, cr_acc);
-        if (tid < K1_LOOK / 16) {                             // look-ahead bytes: only the odd-byte tests
-            const uint32_t off = (uint32_t)K1_TILE + (uint32_t)tid * 16u;
+        __syncwarp();
+        // ---- scan: newline masks of this lane's 17 chunks, kept in registers ------------------------
+        uint32_t mk[(K1_LANE_CHUNKS + 1) / 2];                // two 16-flag masks per register
+        uint32_t hi_acc = 0, cr_acc = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < K1_LANE_CHUNKS; j++) {
+            const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
+            uint32_t m = 0;                                   // bit 8*b + w  <->  byte 4*w + b of the chunk
             if (off < wlen) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
                 hi_acc |= v.x | v.y | v.z | v.w;
-                if ((cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w)) & 0x80808080u)
-                    if (lone_cr_in_chunk(sm.buf, off)) hi_acc |= 0x80u;
+                if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
+                m = k1_chunk_mask(v, off, wlen);
             }
+            cnt += (uint32_t)__popc(m);
+            if (j & 1) mk[j >> 1] |= m << 4; else mk[j >> 1] = m;      // the layout leaves bits 4-7 of each byte free
         }
-        if (cr_acc & 0x80808080u) {                           // CRs present: fine when each is followed by LF
-            for (int it = 0; it < K1_WREGION / 512; it++) {
-                const uint32_t off = (uint32_t)warp * K1_WREGION + (uint32_t)it * 512u + (uint32_t)lane * 16u;
-                if (off < wlen && lone_cr_in_chunk(sm.buf, off)) hi_acc |= 0x80u;
-            }
+        // look-ahead bytes: only the odd-byte tests
+        for (uint32_t off = (uint32_t)K1_TILE + (uint32_t)lane * 16u; off < wlen; off += 512u) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
+            hi_acc |= v.x | v.y | v.z | v.w;
+            if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
         }
-        if (lane == 0) sm.wcount[warp] = wtotal;
-        if (hi_acc & 0x80808080u) sm.tile_high = 1u;          // every line of the tile takes the exact path
-        __syncthreads();
-        // ---- parse ----------------------------------------------------------------------------------
-        if (tid == 0) {
-            uint32_t run = 0, mx = 0;
-            for (int w = 0; w < K1_WARPS; w++) {
-                sm.full_prefix[w] = run;
-                run += sm.wcount[w];
-                mx = sm.wcount[w] > mx ? sm.wcount[w] : mx;
-            }
-            sm.full_prefix[K1_WARPS] = run;
-            sm.max_wcount = mx;
+        if (CHECK_CR && __any_sync(0xffffffffu, (cr_acc & H) != 0u)) {   // CRs present: fine when each is followed by LF
+            for (uint32_t off = (uint32_t)lane * 16u; off < wlen; off += 512u)
+                if (lone_cr_in_chunk(sm.buf, off)) hi_acc |= 0x80u;
         }
-        __syncthreads();
-        const uint32_t n_tile_lines = sm.full_prefix[K1_WARPS];
-        const bool high = sm.tile_high != 0u;
-        const uint32_t n_pass = (sm.max_wcount + K1_WCAP - 1u) / K1_WCAP;
-        for (uint32_t pass = 0; pass < n_pass; pass++) {
-            if (pass > 0) {
-                uint32_t dummy = 0, dummy2 = 0;
-                k1_scan_region(sm, warp, lane, tile, wlen, pass, dummy, dummy2);
-            }
-            if (tid == 0) {
-                uint32_t run = 0;
-                for (int w = 0; w < K1_WARPS; w++) {
-                    const uint32_t done = pass * K1_WCAP;
-                    const uint32_t rem = sm.wcount[w] > done ? sm.wcount[w] - done : 0u;
-                    const uint32_t c = rem < (uint32_t)K1_WCAP ? rem : (uint32_t)K1_WCAP;
-                    sm.pass_count[w] = c;
-                    sm.pass_prefix[w] = run;
-                    run += c;
-                }
-                sm.pass_prefix[K1_WARPS] = run;
-            }
-            __syncthreads();
-            const uint32_t n_pass_lines = sm.pass_prefix[K1_WARPS];
-            for (uint32_t l = (uint32_t)tid; l < n_pass_lines; l += K1_THREADS) {
-                int w = 0;
+        if (__any_sync(0xffffffffu, (hi_acc & H) != 0u)) {    // odd bytes around: every line takes the exact path
+            const uint32_t r = k1_slow_tile(a, sm, cs, lane, n_gq, tile, base, wlen);
+            n_gq = r >> 16;
+            if (lane == 0 && a.tile_nlines) a.tile_nlines[tile] = r & 0xffffu;
+            n_lines += r & 0xffffu;
+            continue;
+        }
+        const bool file_start = tile == 0 && lane == 0 && wlen > 0;
+        if (file_start) cnt++;                                // the first line of the file
+        // ---- order: one prefix sum over the lanes ---------------------------------------------------
+        uint32_t incl = cnt;
 #pragma unroll
-                for (int x = 1; x < K1_WARPS; x++) w += (l >= sm.pass_prefix[x]) ? 1 : 0;
-                const uint32_t k = l - sm.pass_prefix[w];
-                const uint32_t line_idx = sm.full_prefix[w] + pass * K1_WCAP + k;
-                const uint32_t s = sm.wstarts[w][k];
-                uint32_t e;
-                if (k + 1u < sm.pass_count[w]) e = (uint32_t)sm.wstarts[w][k + 1] - 1u;
-                else if (pass == 0u && k + 1u == sm.wcount[w] && w + 1 < K1_WARPS && sm.wcount[w + 1] > 0u)
-                    e = (uint32_t)sm.wstarts[w + 1][0] - 1u;            // the next region's first line follows
-                else e = find_nl(sm.buf, s, wlen);
-                const unsigned long long goff = base + s;
-                if (high || (e == wlen && base + wlen != a.nbytes)) {   // odd bytes, or the line leaves the window
-                    th.general(goff, line_idx);
-                    continue;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t n_tile_lines = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t first_idx = incl - cnt;
+        // ---- list the starts (the first K1_WCAP of them; more -> later passes scan again) ----------------
+        {
+            uint32_t idx = first_idx;
+            if (file_start) { sm.starts[0] = 0xffffu; idx++; }
+#pragma unroll
+            for (int j = 0; j < K1_LANE_CHUNKS; j++) {
+                const uint32_t m = ((j & 1) ? (mk[j >> 1] >> 4) : mk[j >> 1]) & 0x0f0f0f0fu;
+                k1_list_hits(sm.starts, m, (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, idx);
+            }
+        }
+        // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
+        for (uint32_t done = 0; done < n_tile_lines; done += K1_WCAP) {
+            __syncwarp();
+            if (done) {
+                k1_relist(sm, lane, wlen, first_idx + (file_start ? 1u : 0u) - done);   // (wraps below the pass: rejected)
+                __syncwarp();
+            }
+            const uint32_t n_pass = n_tile_lines - done < (uint32_t)K1_WCAP ? n_tile_lines - done : (uint32_t)K1_WCAP;
+            for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
+                const uint32_t l = l0 + (uint32_t)lane;
+                const bool have = l < n_pass;
+                const uint32_t line_idx = done + l;
+                uint32_t s = 0;
+                if (have) {
+                    const uint32_t code = sm.starts[l];       // chunk << 5 | flag bit 8*b + w  ->  byte 4*w + b of the chunk
+                    if (code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
                 }
-                FastLine fl;
-                int st = fast_line<HAS_QUAL>(sm.buf, s, e, a.sites, hint, a.p, all, &fl);
-                if (st == ST_OK) {
-                    th.emit(fl.base, fl.fail, fl.site, goff, line_idx);
-                } else if (st == ST_FALLBACK) {
-                    uint32_t q = atomicAdd(&sm.n_genq, 1u);
-                    if (q < (uint32_t)K1_GENQ) sm.genq[q] = (line_idx << 16) | s;
-                    else th.general(goff, line_idx);
+                bool to_detail = false;
+                if (have) {
+                    to_detail = true;
+                    if (!HAS_QUAL) {
+                        QuickLine q;
+                        const int st = quick_line(sm.buf, s, wlen, a.sites, cc, a.p, ALL, &q);
+                        if (st == ST_SKIP) to_detail = false;
+                        else if (st == ST_OK && !(q.end == wlen && !eof)) {   // (a line that leaves the window goes on)
+                            k1_emit(a, q.base, q.fail, q.site, base + s, line_idx < (uint32_t)K1_MAXLINES ? stage0 + line_idx : ~(size_t)0);
+                            n_parsed++;
+                            to_detail = false;
+                        }
+                    }
+                }
+                const unsigned long long entry = ((unsigned long long)line_idx << 48) | (base + s);
+                n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
+                if (n_dq >= 32u) {                            // leaves both queues below 32
+                    const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
+                    n_dq = r & 0xffffu; n_gq = r >> 16;
                 }
             }
-            __syncthreads();
-            const uint32_t nq = sm.n_genq < (uint32_t)K1_GENQ ? sm.n_genq : (uint32_t)K1_GENQ;
-            for (uint32_t g = (uint32_t)tid; g < nq; g += K1_THREADS) {
-                const uint32_t v = sm.genq[g];
-                th.general(base + (v & 0xffffu), v >> 16);
-            }
-            __syncthreads();
-            if (tid == 0) sm.n_genq = 0;
         }
-        if (tid == 0) {
-            if (a.tile_nlines) a.tile_nlines[tile] = n_tile_lines;
-            sm.n_lines += n_tile_lines;
-        }
-        __syncthreads();                                      // everyone is done with buf before it is refilled
+        if (lane == 0 && a.tile_nlines) a.tile_nlines[tile] = n_tile_lines;
+        n_lines += n_tile_lines;
+    }
+    {
+        const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
+        k1_drain_general(a, sm, cs, lane, r >> 16, true);
     }
     // ---- statistics -------------------------------------------------------------------------------
-    uint32_t np = th.n_parsed, ng = th.n_general;
+    uint32_t np = n_parsed + cs.n_parsed, ng = cs.n_general;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         np += __shfl_xor_sync(0xffffffffu, np, d);
         ng += __shfl_xor_sync(0xffffffffu, ng, d);
     }
     if (lane == 0) {
-        atomicAdd(&sm.n_parsed, (unsigned long long)np);
-        atomicAdd(&sm.n_general, (unsigned long long)ng);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        atomicAdd(&a.st->n_parsed, sm.n_parsed);
-        atomicAdd(&a.st->n_general, sm.n_general);
-        atomicAdd(&a.st->n_lines, sm.n_lines);
+        atomicAdd(&a.st->n_parsed, (unsigned long long)np);
+        atomicAdd(&a.st->n_general, (unsigned long long)ng);
+        atomicAdd(&a.st->n_lines, n_lines);
     }
 }
 
@@ -436,23 +529,31 @@ int k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes) {
     return 1;
 }
 
-int k1_blocks_per_sm(bool has_qual) {
+template <bool Q, bool A>
+static int k1_occupancy() {
     int n = 0;
-    if (has_qual) {
-        cudaFuncSetAttribute(k1_pileup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k1_pileup_kernel<true>, K1_THREADS, sizeof(K1Smem));
-    } else {
-        cudaFuncSetAttribute(k1_pileup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k1_pileup_kernel<false>, K1_THREADS, sizeof(K1Smem));
-    }
+    cudaFuncSetAttribute(k1_pileup_kernel<Q, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k1_pileup_kernel<Q, A>, K1_THREADS, k1_smem_bytes());
     return n;
+}
+
+// resident CTAs per SM (the smallest over the variants, which also sets their shared-memory attribute)
+int k1_blocks_per_sm(bool has_qual) {
+    int n0 = has_qual ? k1_occupancy<true, false>() : k1_occupancy<false, false>();
+    int n1 = has_qual ? k1_occupancy<true, true>() : k1_occupancy<false, true>();
+    return n0 < n1 ? n0 : n1;
 }
 
 int k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks) {
     if (a.n_tiles <= 0) return 0;
-    int grid = a.n_tiles < grid_blocks ? a.n_tiles : grid_blocks;
-    if (a.p.min_base_qual > 0) k1_pileup_kernel<true><<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(a);
-    else k1_pileup_kernel<false><<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(a);
+    const int want = (a.n_tiles + K1_WARPS - 1) / K1_WARPS;
+    const int grid = want < grid_blocks ? want : grid_blocks;
+    const bool q = a.p.min_base_qual > 0, all = a.mode == SNPGPU_MODE_ALL;
+    const size_t sh = k1_smem_bytes();
+    if (q && all) k1_pileup_kernel<true, true><<<grid, K1_THREADS, sh, stream>>>(a);
+    else if (q) k1_pileup_kernel<true, false><<<grid, K1_THREADS, sh, stream>>>(a);
+    else if (all) k1_pileup_kernel<false, true><<<grid, K1_THREADS, sh, stream>>>(a);
+    else k1_pileup_kernel<false, false><<<grid, K1_THREADS, sh, stream>>>(a);
     return 1;
 }
 

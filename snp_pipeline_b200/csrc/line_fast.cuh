@@ -201,6 +201,8 @@ SNP_HD int fast_line(const uint8_t *buf, uint32_t s, uint32_t e, const SiteTable
     out->pos = (int64_t)pos; out->cid = cid; out->site = site; out->ref = (uint8_t)ref;
     if (raw_depth == 0) {                              // pileup.py:226-234 -> ('-', RawDpth)
         if (buf[i] != '\t' && i != e) return ST_FALLBACK;
+        for (uint32_t k = i; k < e; k++)                // the rest is ignored, but a lone CR would end the line
+            if (buf[k] == '\r') return ST_FALLBACK;
         out->base = '-'; out->fail = FAIL_RAWDPTH;
         return ST_OK;
     }

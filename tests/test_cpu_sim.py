@@ -46,7 +46,7 @@ def run_sim(L, text, snps, excl, ps, all_pos, force_general=False):
     row = np.zeros(max(len(snps), 1), dtype=np.uint8)
     cap = buf.size + 2
     lines = np.zeros(cap, dtype=np.uint16)
-    counters = np.zeros(5, dtype=np.uint64)
+    counters = np.zeros(6, dtype=np.uint64)
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data) if a.size else None
     rc = L.cpusim_pileup(ptr(buf), buf.size, blob, ptr(off), len(names), ptr(sc), ptr(sp), len(snps), ptr(ec), ptr(ep),
                          len(excl), ctypes.byref(p), 1 if all_pos else 0, 1 if force_general else 0, ptr(row),
@@ -89,6 +89,8 @@ def test_realistic_text(sim, seed):
     for all_pos in (False, True):
         c = _compare(sim, text, snps, excl, ps, all_pos)
         assert c[2] < c[0] * 0.02 + 5, "the fast path should take nearly every samtools-shaped line"
+        if ps[0] <= 0:
+            assert c[5] > c[1] * 0.9, "the first-tier parser should decide most parsed lines (%d of %d)" % (c[5], c[1])
         _compare(sim, text, snps, excl, ps, all_pos, force_general=True)
 
 
@@ -113,6 +115,56 @@ def test_nasty_text(sim, seed):
     for ps in (PARAM_SETS[seed % len(PARAM_SETS)], PARAM_SETS[(seed + 2) % len(PARAM_SETS)]):
         for all_pos in (False, True):
             _compare(sim, text, snps, excl, ps, all_pos)
+
+
+def _boundary_line(rng, pos):
+    """Lines around the first-tier parser's decision boundary (csrc/line_quick.cuh): reference base winning by a
+    hair or tied, the reference letter written out, every kind of '^' partner, markers at word boundaries."""
+    ref = rng.choice("ACGTNacgtn")
+    depth = rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 40])
+    n_oth = rng.choice([0, 0, 1, depth // 2, (depth + 1) // 2, max(0, depth // 2 - 1), depth])
+    syms = [rng.choice(".,") for _ in range(depth)]
+    for i in rng.sample(range(depth), min(n_oth, depth)):
+        syms[i] = rng.choice("ACGTNacgtn*" + ref.upper() + ref.lower() + "><RYk#7")
+    toks = []
+    for c in syms:
+        x = rng.random()
+        if x < 0.12:
+            toks.append("^" + rng.choice("KIUS!~]+-$^.,*" + ref.upper() + ref.lower()))
+        toks.append(c)
+        if x > 0.9:
+            toks.append("$")
+        if 0.5 < x < 0.52:
+            toks.append(rng.choice("+-") + rng.choice(["1A", "2ac", "", "0", "3GGG"]))
+    bases = "".join(toks)
+    if rng.random() < 0.05:
+        bases += "^"
+    nq = depth + rng.choice([0, 0, 0, 0, 0, 0, 1, -1, 2])
+    quals = "".join(chr(rng.randint(33, 126)) for _ in range(max(nq, 0)))
+    tail = rng.choice(["\n"] * 8 + ["\r\n", " \n"])
+    return "%s\t%d\t%s\t%d\t%s\t%s%s" % (linegen.CHROM, pos, ref, depth, bases, quals, tail)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_first_tier_boundary(sim, seed):
+    rng = random.Random(700 + seed)
+    n = 1500
+    op = orc.make_params()
+    lines = []
+    for pos in range(1, n + 1):
+        ln = _boundary_line(rng, pos)
+        if orc.line_report(ln.rstrip("\n").encode(), op)["status"] == 0:
+            lines.append(ln)
+    text = "".join(lines).encode()
+    if seed % 3 == 2:
+        text = text[:-1]
+    snps = [(linegen.CHROM, p) for p in rng.sample(range(1, n + 10), 300)]
+    quick = 0
+    for ps in (PARAM_SETS[seed % 2], PARAM_SETS[3], PARAM_SETS[5], PARAM_SETS[6]):
+        for all_pos in (False, True):
+            c = _compare(sim, text, snps, [], ps, all_pos)
+            quick += int(c[5])
+    assert quick > 0
 
 
 def test_reference_file_vectors(sim, ref_files):
