@@ -22,15 +22,16 @@ struct PileupStatusDev {
 };
 
 // Tile geometry of the pileup kernel: every warp is its own pipeline.
-constexpr int K1_LANE_CHUNKS = 17;             // 16-byte chunks one lane scans for newlines ...
-constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... = 272 bytes = 68 words: quarter warps hit disjoint banks
-constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // 8704 bytes of text whose line starts one tile owns
+constexpr int K1_LANE_CHUNKS = 21;             // 16-byte chunks one lane scans for newlines ...
+constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
+constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
 constexpr int K1_LOOK     = 1024;              // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_WARPS    = 5;                 // independent warps per CTA
+constexpr int K1_WARPS    = 4;                 // independent warps per CTA
 constexpr int K1_THREADS  = 32 * K1_WARPS;
-constexpr int K1_CTAS_PER_SM = 4;              // 20 warps x 10.6 KiB of shared memory per SM
+constexpr int K1_CTAS_PER_SM = 4;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
 constexpr int K1_WCAP     = 256;               // line starts a warp lists per pass (more -> another pass)
+constexpr int K1_LHCAP    = 12;                // line starts one lane lists per tile (more -> byte-wise path)
 constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
 constexpr int K1_QCAP     = 64;                // per-warp queue slots (drained whenever 32 are filled)
 constexpr int K1_MAXLINES = K1_TILE / 8;       // all-positions mode: a line that parses has >= 8 bytes

@@ -9,9 +9,9 @@
 //   * the tile (+1 KiB of look-ahead so the last owned line is complete) is staged into the warp's slice of
 //     shared memory by ONE 1-D bulk async copy (TMA engine, mbarrier completion); the other resident warps
 //     compute while this one waits;
-//   * scan: lane L owns bytes [272 L, 272 L + 272) of the tile (a 68-word stride, so the 16-byte loads of a
-//     quarter warp fall into disjoint banks), tests them for '\n' with SWAR arithmetic and keeps the 17 hit
-//     masks in registers; ONE warp prefix sum over the per-lane counts then orders all line starts of the tile;
+//   * scan: lane L owns K1_LANE_BYTES consecutive bytes of the tile (a stride of 4 mod 8 words, so the 16-byte
+//     loads of a quarter warp fall into disjoint banks), tests them for '\n' with SWAR arithmetic and lists its
+//     hits; ONE warp prefix sum over the per-lane counts then orders all line starts of the tile;
 //   * parse: one lane per line, 32 lines in lock step, through the first-tier parser (line_quick.cuh);
 //   * the few lines it declines are queued per warp (by file offset) and, whenever 32 have piled up, run densely
 //     through the exact-tally parser (line_fast.cuh) and, from there, the any-input parser (line_general.cuh),
@@ -29,7 +29,8 @@ namespace snpgpu {
 
 struct K1Warp {                                 // one warp's slice of shared memory
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
-    uint16_t starts[K1_WCAP];                   // line starts (buffer offsets) of the current pass, file order
+    uint16_t starts[K1_WCAP];                   // line starts of the current pass, file order: chunk << 5 | flag bit
+    uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
     uint32_t cname[K1_NAMEW];                   // name + tab of the contig the warp expects (ContigCache::name4)
     unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh:  (line index in its tile << 48) | file offset
     unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
@@ -257,18 +258,19 @@ __device__ __forceinline__ uint32_t k1_chunk_mask(const uint4 v, uint32_t off, u
 }
 
 // appends the line starts flagged in m (chunk number `chunk`) to the pass's list as (chunk << 5 | flag bit)
-__device__ __forceinline__ void k1_list_hits(uint16_t *starts, uint32_t m, uint32_t chunk, uint32_t &idx) {
+// (slots at or above cap are counted but not written)
+__device__ __forceinline__ void k1_list_hits(uint16_t *list, uint32_t cap, uint32_t m, uint32_t chunk, uint32_t &idx) {
     if (m == 0u) return;
     const uint32_t chunk5 = chunk << 5;
     if ((m & (m - 1u)) == 0u) {
-        if (idx < (uint32_t)K1_WCAP) starts[idx] = (uint16_t)(chunk5 | (uint32_t)ctz32(m));
+        if (idx < cap) list[idx] = (uint16_t)(chunk5 | (uint32_t)ctz32(m));
         idx++;
     } else {                                                  // lines shorter than 16 bytes: in byte order
 #pragma unroll 1
         for (uint32_t pos = 0; pos < 16u; pos++) {
             const uint32_t f = 8u * (pos & 3u) + (pos >> 2);
             if ((m >> f) & 1u) {
-                if (idx < (uint32_t)K1_WCAP) starts[idx] = (uint16_t)(chunk5 | f);
+                if (idx < cap) list[idx] = (uint16_t)(chunk5 | f);
                 idx++;
             }
         }
@@ -281,7 +283,7 @@ __device__ __noinline__ void k1_relist(K1Warp &sm, int lane, uint32_t wlen, uint
         const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
         if (off >= wlen) break;
         const uint32_t m = k1_chunk_mask(*reinterpret_cast<const uint4 *>(sm.buf + off), off, wlen);
-        k1_list_hits(sm.starts, m, (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, idx);
+        k1_list_hits(sm.starts, K1_WCAP, m, (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, idx);
     }
 }
 
@@ -342,22 +344,20 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         if (bulk) { mbar_wait(&sm.bar, parity); parity ^= 1u; }
         __syncwarp();
-        // ---- scan: newline masks of this lane's 17 chunks, kept in registers ------------------------
-        uint32_t mk[(K1_LANE_CHUNKS + 1) / 2];                // two 16-flag masks per register
+        // ---- scan: every lane lists the line starts of its chunks as it finds them -------------------
         uint32_t hi_acc = 0, cr_acc = 0, cnt = 0;
+        uint16_t *myhits = sm.lanehits + lane * K1_LHCAP;
 #pragma unroll
         for (int j = 0; j < K1_LANE_CHUNKS; j++) {
             const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
-            uint32_t m = 0;                                   // bit 8*b + w  <->  byte 4*w + b of the chunk
             if (off < wlen) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
                 hi_acc |= v.x | v.y | v.z | v.w;
                 if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
-                m = k1_chunk_mask(v, off, wlen);
+                k1_list_hits(myhits, K1_LHCAP, k1_chunk_mask(v, off, wlen), (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, cnt);
             }
-            cnt += (uint32_t)__popc(m);
-            if (j & 1) mk[j >> 1] |= m << 4; else mk[j >> 1] = m;      // the layout leaves bits 4-7 of each byte free
         }
+        if (cnt > (uint32_t)K1_LHCAP) hi_acc |= 0x80u;        // a crowd of tiny lines: the byte-wise path sorts it out
         // look-ahead bytes: only the odd-byte tests
         for (uint32_t off = (uint32_t)K1_TILE + (uint32_t)lane * 16u; off < wlen; off += 512u) {
             const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
@@ -386,14 +386,13 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         const uint32_t n_tile_lines = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t first_idx = incl - cnt;
-        // ---- list the starts (the first K1_WCAP of them; more -> later passes scan again) ----------------
+        // ---- the warp's list, file order (the first K1_WCAP starts; more -> later passes scan again) -----
         {
-            uint32_t idx = first_idx;
-            if (file_start) { sm.starts[0] = 0xffffu; idx++; }
-#pragma unroll
-            for (int j = 0; j < K1_LANE_CHUNKS; j++) {
-                const uint32_t m = ((j & 1) ? (mk[j >> 1] >> 4) : mk[j >> 1]) & 0x0f0f0f0fu;
-                k1_list_hits(sm.starts, m, (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, idx);
+            const uint32_t skip = file_start ? 1u : 0u;
+            if (file_start) sm.starts[0] = 0xffffu;
+            for (uint32_t k = 0; k + skip < cnt; k++) {
+                const uint32_t idx = first_idx + skip + k;
+                if (idx < (uint32_t)K1_WCAP) sm.starts[idx] = myhits[k];
             }
         }
         // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
