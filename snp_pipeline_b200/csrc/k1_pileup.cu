@@ -347,17 +347,35 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         // ---- scan: every lane lists the line starts of its chunks as it finds them -------------------
         uint32_t hi_acc = 0, cr_acc = 0, cnt = 0;
         uint16_t *myhits = sm.lanehits + lane * K1_LHCAP;
+        if (wlen > (uint32_t)K1_TILE) {                       // a whole tile: no chunk needs a bounds test
+            uint32_t multi = 0;
 #pragma unroll
-        for (int j = 0; j < K1_LANE_CHUNKS; j++) {
-            const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
-            if (off < wlen) {
+            for (int j = 0; j < K1_LANE_CHUNKS; j++) {
+                const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
+                const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
+                hi_acc |= v.x | v.y | v.z | v.w;
+                if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
+                const uint32_t NL = 0x0a0a0a0au, K = 0x7f7f7f7fu;
+                const uint32_t x0 = (v.x ^ NL) + K, x1 = (v.y ^ NL) + K, x2 = (v.z ^ NL) + K, x3 = (v.w ^ NL) + K;
+                const uint32_t m = ((~x0 & H) >> 7) | ((~x1 & H) >> 6) | ((~x2 & H) >> 5) | ((~x3 & H) >> 4);
+                const uint32_t code = (((uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j) << 5) | ((uint32_t)__ffs((int)m) - 1u);
+                if (m != 0u && cnt < (uint32_t)K1_LHCAP) myhits[cnt] = (uint16_t)code;   // predicated, no branch
+                cnt += m != 0u ? 1u : 0u;
+                multi |= m & (m - 1u);                        // two starts within 16 bytes
+            }
+            if (multi) hi_acc |= 0x80u;                       // tiny lines: the byte-wise path sorts them out
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < K1_LANE_CHUNKS; j++) {
+                const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
+                if (off >= wlen) break;
                 const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
                 hi_acc |= v.x | v.y | v.z | v.w;
                 if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
                 k1_list_hits(myhits, K1_LHCAP, k1_chunk_mask(v, off, wlen), (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, cnt);
             }
         }
-        if (cnt > (uint32_t)K1_LHCAP) hi_acc |= 0x80u;        // a crowd of tiny lines: the byte-wise path sorts it out
+        if (cnt > (uint32_t)K1_LHCAP) hi_acc |= 0x80u;        // a crowd of short lines: likewise
         // look-ahead bytes: only the odd-byte tests
         for (uint32_t off = (uint32_t)K1_TILE + (uint32_t)lane * 16u; off < wlen; off += 512u) {
             const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
@@ -403,9 +421,45 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 __syncwarp();
             }
             const uint32_t n_pass = n_tile_lines - done < (uint32_t)K1_WCAP ? n_tile_lines - done : (uint32_t)K1_WCAP;
+            // ---- order the pass by line length (counting sort, 16 classes of 8 bytes): the 32 lines a warp
+            //      parses in lock step then run their loops about equally long.  perm/hist reuse lanehits. ----
+            uint8_t *perm = reinterpret_cast<uint8_t *>(sm.lanehits);
+            uint32_t *hist = reinterpret_cast<uint32_t *>(sm.lanehits) + 64;
+            if (lane < 16) hist[lane] = 0u;
+            __syncwarp();
+            uint32_t keys = 0;                                // 4 bits per line of this lane
+            unsigned long long ranks = 0;                     // 8 bits per line
+            for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u) {
+                const uint32_t c0 = sm.starts[l], c1 = l + 1u < n_pass ? sm.starts[l + 1u] : 0xffffu;
+                uint32_t key = 15u;
+                if (c0 != 0xffffu && c1 != 0xffffu) {         // bytes between consecutive starts
+                    const uint32_t len = ((c1 >> 5) - (c0 >> 5)) * 16u + ((c1 & 7u) - (c0 & 7u)) * 4u + (((c1 >> 3) & 3u) - ((c0 >> 3) & 3u));
+                    key = len < 32u ? 0u : (len - 32u) >> 3;
+                    key = key > 15u ? 15u : key;
+                }
+                const uint32_t r = atomicAdd(&hist[key], 1u);
+                keys |= key << (4u * k);
+                ranks |= (unsigned long long)r << (8u * k);
+            }
+            __syncwarp();
+            {
+                const uint32_t v = lane < 16 ? hist[lane] : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                __syncwarp();
+                if (lane < 16) hist[lane] = inc - v;
+            }
+            __syncwarp();
+            for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u)
+                perm[hist[(keys >> (4u * k)) & 15u] + (uint32_t)((ranks >> (8u * k)) & 0xffu)] = (uint8_t)l;
+            __syncwarp();
             for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
-                const uint32_t l = l0 + (uint32_t)lane;
-                const bool have = l < n_pass;
+                const bool have = l0 + (uint32_t)lane < n_pass;
+                const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
                 const uint32_t line_idx = done + l;
                 uint32_t s = 0;
                 if (have) {
