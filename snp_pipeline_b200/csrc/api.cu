@@ -39,7 +39,7 @@ struct snpgpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t     launches = 0;
     std::string  err;
-    DevBuf status, site_cells, stage, tile_nlines, tile_prefix, arena, stats;
+    DevBuf status, site_cells, tile_state, tile_first, arena, stats;
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
@@ -121,7 +121,7 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->status, &ctx->site_cells, &ctx->stage, &ctx->tile_nlines, &ctx->tile_prefix, &ctx->arena,
+    DevBuf *all[] = {&ctx->status, &ctx->site_cells, &ctx->tile_state, &ctx->tile_first, &ctx->arena,
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
                      &ctx->synth_tmp, &ctx->synth_n};
@@ -273,9 +273,9 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     CK(ctx->site_cells.ensure((sites->n_unique + 1) * sizeof(unsigned long long)));
     CK(ctx->arena.ensure(ctx->arena_want));
     if (want_lines) {
-        CK(ctx->stage.ensure((size_t)std::max(n_tiles, 1) * K1_MAXLINES * sizeof(uint16_t)));
-        CK(ctx->tile_nlines.ensure(((size_t)n_tiles + 1) * sizeof(uint32_t)));
-        CK(ctx->tile_prefix.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+        CK(ctx->tile_state.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+        CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->tile_state.p, 0, ((size_t)n_tiles + 1) * sizeof(unsigned long long), st));
     }
     CK(cudaMemsetAsync(ctx->status.p, 0, sizeof(PileupStatusDev), st));
     CK(cudaMemsetAsync(ctx->status.p, 0xff, sizeof(unsigned long long), st));     // first_error = ~0
@@ -288,8 +288,10 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     a.mode = mode;
     a.n_tiles = n_tiles;
     a.site_cells = (unsigned long long *)ctx->site_cells.p;
-    a.line_stage = want_lines ? (uint16_t *)ctx->stage.p : nullptr;
-    a.tile_nlines = want_lines ? (uint32_t *)ctx->tile_nlines.p : nullptr;
+    a.line_out = want_lines ? line_out_dev : nullptr;
+    a.line_out_cap = want_lines ? (unsigned long long)line_out_cap : 0ull;
+    a.tile_state = want_lines ? (unsigned long long *)ctx->tile_state.p : nullptr;
+    a.tile_first = want_lines ? (unsigned long long *)ctx->tile_first.p : nullptr;
     a.st = (PileupStatusDev *)ctx->status.p;
     a.arena = (uint8_t *)ctx->arena.p;
     a.arena_cap = ctx->arena.cap;
@@ -300,9 +302,6 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     }
     if (sites->n_snp)
         ctx->launches += (uint64_t)k1_launch_row(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev);
-    if (want_lines)
-        ctx->launches += (uint64_t)k1_launch_lines(st, a.line_stage, a.tile_nlines, n_tiles,
-                                                   (unsigned long long *)ctx->tile_prefix.p, line_out_dev, line_out_cap);
     if (stats_dev) ctx->launches += (uint64_t)k1_launch_stats(st, a.st, stats_dev);
     CK(cudaGetLastError());
     return SNPGPU_OK;

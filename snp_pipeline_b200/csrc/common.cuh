@@ -32,9 +32,11 @@ constexpr int K1_THREADS  = 32 * K1_WARPS;
 constexpr int K1_CTAS_PER_SM = 4;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
 constexpr int K1_WCAP     = 256;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = 12;                // line starts one lane lists per tile (more -> byte-wise path)
+constexpr int K1_RES_OFF  = 160;               // lanehits[K1_RES_OFF ..]: a parsed tile's per-line results (in front of it:
+                                               // the length sort's permutation and histogram, see k1_pileup.cu)
+constexpr int K1_RES_CAP  = 32 * K1_LHCAP - K1_RES_OFF;   // lines per tile that fit there (more -> written directly)
 constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
 constexpr int K1_QCAP     = 64;                // per-warp queue slots (drained whenever 32 are filled)
-constexpr int K1_MAXLINES = K1_TILE / 8;       // all-positions mode: a line that parses has >= 8 bytes
 
 struct PileupArgs {
     const uint8_t      *text;          // 16-byte aligned
@@ -45,8 +47,10 @@ struct PileupArgs {
     int                 n_tiles;
     unsigned long long *site_cells;    // n_unique, zero-initialised: ((line offset + 1) << 8) | cell  (atomicMax:
                                        // the last line in file order wins, like the dict of call_consensus.py:169)
-    uint16_t           *line_stage;    // [n_tiles][K1_MAXLINES] or null: cell | fail << 8 per line of the tile
-    uint32_t           *tile_nlines;   // [n_tiles] or null
+    uint16_t           *line_out;      // null, or one uint16 per line in file order: cell | fail << 8
+    unsigned long long  line_out_cap;
+    unsigned long long *tile_state;    // [n_tiles], zero-initialised: decoupled look-back over the tiles' line counts
+    unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (set by the warp that owns it)
     PileupStatusDev    *st;
     uint8_t            *arena;
     unsigned long long  arena_cap;

@@ -11,8 +11,6 @@ int    k1_blocks_per_sm(bool has_qual);
 int    k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks);
 int    k1_launch_row(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique,
                      size_t n_snp, uint8_t *row_out_dev);
-int    k1_launch_lines(cudaStream_t stream, const uint16_t *line_stage, const uint32_t *tile_nlines, int n_tiles,
-                       unsigned long long *tile_prefix, uint16_t *line_out_dev, size_t line_out_cap);
 int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
 int    k1_launch_stats(cudaStream_t stream, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev);
 

@@ -17,8 +17,8 @@
 //     through the exact-tally parser (line_fast.cuh) and, from there, the any-input parser (line_general.cuh),
 //     both on the text where it lies in global memory (an L2 hit);
 //   * results: an atomicMax per hit site keeps the LAST line of a position in file order (the dict overwrite
-//     of call_consensus.py:169-176); in all-positions mode a uint16 per line is staged per tile and compacted
-//     to file order by a second tiny kernel.
+//     of call_consensus.py:169-176); in all-positions mode one uint16 per line goes straight to its file-order
+//     slot: the index of a tile's first line comes from a decoupled look-back over the tiles' line counts.
 // Algorithmic traffic: every text byte read once (+12 % look-ahead re-read, an L2 hit), 2 B written per line.
 #include "internal.h"
 #include "line_fast.cuh"
@@ -81,22 +81,65 @@ __device__ __forceinline__ void k1_report(const PileupArgs &a, unsigned long lon
 }
 
 // call_consensus.py:165-176: Region failure, '-' substitution, keep the cell for the snplist gather.
-// stage_idx: slot of the line in line_stage (tile * K1_MAXLINES + line index in the tile), ~0 for none.
-__device__ __forceinline__ void k1_emit(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
-                                        unsigned long long goff, size_t stage_idx) {
+// Returns the line's result word: matrix cell | fail mask << 8.
+__device__ __forceinline__ uint16_t k1_cell(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                            unsigned long long goff) {
     unsigned flags = site >= 0 ? a.sites.flags[site] : 0u;
     if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
     unsigned cell = (fail || base_ch == '*') ? (unsigned)'-' : base_ch;
     if (flags & SITE_SNP) atomicMax(&a.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
-    if (a.line_stage && stage_idx != ~(size_t)0) a.line_stage[stage_idx] = (uint16_t)(cell | (fail << 8));
+    return (uint16_t)(cell | (fail << 8));
 }
 
-// slot in line_stage of the line that starts at file offset goff and is the line_idx-th of its tile (the tile
-// holding the byte in front of it)
-__device__ __forceinline__ size_t k1_stage_idx(unsigned long long goff, uint32_t line_idx) {
-    if (line_idx >= (uint32_t)K1_MAXLINES) return ~(size_t)0;
+// the same, stored at the line's file-order index `slot` of line_out (~0 for none)
+__device__ __forceinline__ void k1_emit(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                        unsigned long long goff, unsigned long long slot) {
+    const uint16_t v = k1_cell(a, base_ch, fail, site, goff);
+    if (slot < a.line_out_cap) a.line_out[slot] = v;
+}
+
+// file-order index of the line that starts at file offset goff and is the line_idx-th of its tile (the tile
+// holding the byte in front of it).  Only the warp that owns the tile asks, after it has set tile_first.
+__device__ __forceinline__ unsigned long long k1_line_slot(const PileupArgs &a, unsigned long long goff, uint32_t line_idx) {
+    if (!a.line_out) return ~0ull;
     const unsigned long long tile = goff ? (goff - 1ull) / (unsigned long long)K1_TILE : 0ull;
-    return (size_t)tile * K1_MAXLINES + line_idx;
+    return a.tile_first[tile] + line_idx;
+}
+
+// Decoupled look-back over the tiles' line counts.  One 64-bit word per tile carries a 2-bit state (0 nothing
+// yet, 1 the tile's own count, 2 the count of all tiles up to and including it) and the value.
+// k1_tile_publish: tile `tile` owns n lines (right after its scan).  k1_tile_resolve (all 32 lanes): how many lines
+// the earlier tiles own, i.e. the file-order index of this tile's first line; also recorded in tile_first.
+// Every warp publishes its own count before it waits for anybody, tiles are handed out in increasing order and
+// all warps are resident, so the wait always ends; the kernel resolves a tile only after parsing it, when the
+// neighbours have long published, so it rarely waits at all.
+__device__ __forceinline__ void k1_tile_publish(const PileupArgs &a, int tile, uint32_t n) {
+    volatile unsigned long long *st = a.tile_state;
+    st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n;
+}
+
+__device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane) {
+    volatile unsigned long long *st = a.tile_state;
+    const unsigned long long UPTO = 2ull << 62, VAL = (1ull << 62) - 1ull;
+    unsigned long long before = 0;
+    if (tile > 0) {
+        for (int j = tile - 1;; j -= 32) {                    // lane L looks at tile j - L
+            const int t = j - lane;
+            unsigned long long v = UPTO;                      // in front of tile 0: nothing
+            if (t >= 0) { do { v = st[t]; } while ((v >> 62) == 0ull); }
+            const uint32_t upto = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+            const int stop = upto ? __ffs((int)upto) - 1 : 31;    // nearest tile that knows its running total
+            unsigned long long c = lane <= stop ? (v & VAL) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+            before += c;
+            if (upto) break;
+        }
+        if (lane == 0) st[tile] = UPTO | (before + (unsigned long long)n);
+    }
+    if (lane == 0) a.tile_first[tile] = before;
+    __syncwarp();
+    return before;
 }
 
 // third tier: the exact any-input parser, on the text where it lies in global memory
@@ -133,7 +176,7 @@ __device__ __noinline__ void k1_general(const PileupArgs &a, K1Cold &cs, unsigne
         int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
         site = site_find(a.sites, cid, r.pos);
     }
-    k1_emit(a, r.base, r.fail, site, goff, k1_stage_idx(goff, line_idx));
+    k1_emit(a, r.base, r.fail, site, goff, k1_line_slot(a, goff, line_idx));
     cs.n_parsed++;
 }
 
@@ -153,7 +196,7 @@ __device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned
     FastLine fl;
     const int st = fast_line<HAS_QUAL>(buf, s, s + n, a.sites, cs.hint, a.p, ALL, &fl);
     if (st == ST_OK) {
-        k1_emit(a, fl.base, fl.fail, fl.site, goff, k1_stage_idx(goff, line_idx));
+        k1_emit(a, fl.base, fl.fail, fl.site, goff, k1_line_slot(a, goff, line_idx));
         cs.n_parsed++;
     }
     return st == ST_FALLBACK;
@@ -224,6 +267,10 @@ __device__ __noinline__ uint32_t k1_slow_tile(const PileupArgs &a, K1Warp &sm, K
         if (lane >= d) incl += o;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (a.line_out) {
+        if (lane == 0) k1_tile_publish(a, tile, total);
+        k1_tile_resolve(a, tile, total, lane);
+    }
     uint32_t idx = incl - cnt, cur = lo;
     bool pending_first = first;
     while (__any_sync(0xffffffffu, cnt > 0u)) {
@@ -309,6 +356,27 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     ContigCache cc;
     contig_cache_load(a.sites, 0, sm.cname, K1_NAMEW, &cc);   // every lane writes the same words
     __syncwarp();
+    // Per-line results of the tile just parsed wait in shared memory (the tail of lanehits) until the file-order
+    // index of the tile's first line is known -- resolved one tile later, while the next window is in flight.
+    uint16_t *res = sm.lanehits + K1_RES_OFF;
+    int pend_tile = -1;                                       // tile whose results sit in res
+    uint32_t pend_n = 0;
+    bool pend_known = false;
+    unsigned long long pend_first = 0;
+    auto resolve_pending = [&]() {                            // (needed before any queued line of that tile is emitted)
+        if (pend_tile >= 0 && !pend_known) { pend_first = k1_tile_resolve(a, pend_tile, pend_n, lane); pend_known = true; }
+    };
+    auto flush_pending = [&]() {
+        if (pend_tile < 0) return;
+        resolve_pending();
+        __syncwarp();
+        for (uint32_t i = (uint32_t)lane; i < pend_n; i += 32u) {
+            const uint16_t v = res[i];                        // 0xffff: the line went to a queue and is emitted from there
+            if (v != 0xffffu && pend_first + i < a.line_out_cap) a.line_out[pend_first + i] = v;
+        }
+        __syncwarp();
+        pend_tile = -1;
+    };
 
     for (int tile = gwarp; tile < a.n_tiles; tile += n_gwarps) {
         {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
@@ -326,7 +394,6 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         const uint32_t wlen = left < (unsigned long long)(K1_TILE + K1_LOOK) ? (uint32_t)left : (uint32_t)(K1_TILE + K1_LOOK);
         const uint32_t bulk = wlen & ~15u;
         const bool eof = left <= (unsigned long long)(K1_TILE + K1_LOOK);
-        const size_t stage0 = (size_t)tile * K1_MAXLINES;
         // ---- stage the window ---------------------------------------------------------------------
         __syncwarp();                                         // every lane is done with the previous window
         if (lane == 0 && bulk) {
@@ -342,6 +409,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
+        flush_pending();                                      // the previous tile's results, while this window loads
         if (bulk) { mbar_wait(&sm.bar, parity); parity ^= 1u; }
         __syncwarp();
         // ---- scan: every lane lists the line starts of its chunks as it finds them -------------------
@@ -389,7 +457,6 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         if (__any_sync(0xffffffffu, (hi_acc & H) != 0u)) {    // odd bytes around: every line takes the exact path
             const uint32_t r = k1_slow_tile(a, sm, cs, lane, n_gq, tile, base, wlen);
             n_gq = r >> 16;
-            if (lane == 0 && a.tile_nlines) a.tile_nlines[tile] = r & 0xffffu;
             n_lines += r & 0xffffu;
             continue;
         }
@@ -404,6 +471,18 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         const uint32_t n_tile_lines = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t first_idx = incl - cnt;
+        // per-line results: published count now, index of the first line later (see flush_pending)
+        bool buffered = false;
+        unsigned long long slot0 = ~0ull - 0xffffull;
+        if (a.line_out) {
+            if (lane == 0) k1_tile_publish(a, tile, n_tile_lines);
+            if (n_tile_lines <= (uint32_t)K1_RES_CAP) {
+                buffered = true;
+                pend_tile = tile; pend_n = n_tile_lines; pend_known = false;
+            } else {
+                slot0 = k1_tile_resolve(a, tile, n_tile_lines, lane);
+            }
+        }
         // ---- the warp's list, file order (the first K1_WCAP starts; more -> later passes scan again) -----
         {
             const uint32_t skip = file_start ? 1u : 0u;
@@ -412,6 +491,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 const uint32_t idx = first_idx + skip + k;
                 if (idx < (uint32_t)K1_WCAP) sm.starts[idx] = myhits[k];
             }
+        }
+        if (buffered) {                                       // (res overlays the lane lists just copied)
+            __syncwarp();
+            for (uint32_t i = (uint32_t)lane; i < n_tile_lines; i += 32u) res[i] = 0xffffu;
         }
         // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
         for (uint32_t done = 0; done < n_tile_lines; done += K1_WCAP) {
@@ -474,7 +557,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         const int st = quick_line(sm.buf, s, wlen, a.sites, cc, a.p, ALL, &q);
                         if (st == ST_SKIP) to_detail = false;
                         else if (st == ST_OK && !(q.end == wlen && !eof)) {   // (a line that leaves the window goes on)
-                            k1_emit(a, q.base, q.fail, q.site, base + s, line_idx < (uint32_t)K1_MAXLINES ? stage0 + line_idx : ~(size_t)0);
+                            const uint16_t v = k1_cell(a, q.base, q.fail, q.site, base + s);
+                            if (buffered) res[line_idx] = v;
+                            else if (slot0 + line_idx < a.line_out_cap) a.line_out[slot0 + line_idx] = v;
                             n_parsed++;
                             to_detail = false;
                         }
@@ -483,15 +568,16 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 const unsigned long long entry = ((unsigned long long)line_idx << 48) | (base + s);
                 n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
                 if (n_dq >= 32u) {                            // leaves both queues below 32
+                    resolve_pending();
                     const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
                     n_dq = r & 0xffffu; n_gq = r >> 16;
                 }
             }
         }
-        if (lane == 0 && a.tile_nlines) a.tile_nlines[tile] = n_tile_lines;
         n_lines += n_tile_lines;
     }
     {
+        flush_pending();
         const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
         k1_drain_general(a, sm, cs, lane, r >> 16, true);
     }
@@ -516,39 +602,6 @@ __global__ void k1_row_kernel(const unsigned long long *site_cells, const int32_
     if (k >= n_snp) return;
     unsigned long long c = site_cells[snp_unique[k]];
     row_out[k] = c ? (uint8_t)(c & 0xffu) : (uint8_t)'-';
-}
-
-// ---- per-line results: staged per tile -> file order -----------------------------------------------------
-__global__ void k1_tile_prefix_kernel(const uint32_t *tile_nlines, int n_tiles, unsigned long long *tile_prefix) {
-    __shared__ unsigned long long part[1024];
-    const int tid = threadIdx.x;
-    const int per = (n_tiles + 1023) / 1024;
-    const int lo = tid * per, hi = min(lo + per, n_tiles);
-    unsigned long long s = 0;
-    for (int i = lo; i < hi; i++) s += tile_nlines[i];
-    part[tid] = s;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        unsigned long long v = tid >= d ? part[tid - d] : 0ull;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    unsigned long long run = part[tid] - s;
-    for (int i = lo; i < hi; i++) { tile_prefix[i] = run; run += tile_nlines[i]; }
-    if (tid == 1023) tile_prefix[n_tiles] = part[1023];
-}
-
-__global__ void k1_lines_kernel(const uint16_t *line_stage, const uint32_t *tile_nlines,
-                                const unsigned long long *tile_prefix, int n_tiles, uint16_t *line_out, size_t cap) {
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t n = tile_nlines[tile];
-        if (n > (uint32_t)K1_MAXLINES) n = K1_MAXLINES;       // more lines than that: one of them raised
-        const unsigned long long o = tile_prefix[tile];
-        const uint16_t *src = line_stage + (size_t)tile * K1_MAXLINES;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-            if (o + i < cap) line_out[o + i] = src[i];
-    }
 }
 
 __global__ void k1_stats_kernel(const PileupStatusDev *st, snpgpu_pileup_stats *out) {
@@ -615,15 +668,6 @@ int k1_launch_row(cudaStream_t stream, const unsigned long long *site_cells, con
     if (!n_snp) return 0;
     k1_row_kernel<<<(unsigned)((n_snp + 255) / 256), 256, 0, stream>>>(site_cells, snp_unique, n_snp, row_out_dev);
     return 1;
-}
-
-int k1_launch_lines(cudaStream_t stream, const uint16_t *line_stage, const uint32_t *tile_nlines, int n_tiles,
-                    unsigned long long *tile_prefix, uint16_t *line_out_dev, size_t line_out_cap) {
-    if (n_tiles <= 0) return 0;
-    k1_tile_prefix_kernel<<<1, 1024, 0, stream>>>(tile_nlines, n_tiles, tile_prefix);
-    int grid = n_tiles < 148 * 8 ? n_tiles : 148 * 8;
-    k1_lines_kernel<<<grid, 128, 0, stream>>>(line_stage, tile_nlines, tile_prefix, n_tiles, line_out_dev, line_out_cap);
-    return 2;
 }
 
 int k1_launch_stats(cudaStream_t stream, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev) {
