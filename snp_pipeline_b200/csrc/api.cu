@@ -39,7 +39,7 @@ struct snpgpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t     launches = 0;
     std::string  err;
-    DevBuf status, site_cells, tile_state, tile_first, arena, stats;
+    DevBuf k1_zero, tile_first, arena, stats;   // k1_zero: status | tile_state | site_cells, cleared by one memset per call
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
@@ -121,7 +121,7 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->status, &ctx->site_cells, &ctx->tile_state, &ctx->tile_first, &ctx->arena,
+    DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->arena,
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
                      &ctx->synth_tmp, &ctx->synth_n};
@@ -269,17 +269,16 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     cudaStream_t st = ctx->stream;
     const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out_dev != nullptr;
-    CK(ctx->status.ensure(sizeof(PileupStatusDev)));
-    CK(ctx->site_cells.ensure((sites->n_unique + 1) * sizeof(unsigned long long)));
+    // per-call scratch that starts as zeros, in one allocation: status | tile_state | site_cells
+    const size_t z_status = 0, z_tiles = 256;
+    const size_t z_cells = z_tiles + (want_lines ? (((size_t)n_tiles + 1) * sizeof(unsigned long long) + 255) & ~(size_t)255 : 0);
+    const size_t z_total = z_cells + (sites->n_unique + 1) * sizeof(unsigned long long);
+    static_assert(sizeof(PileupStatusDev) <= 256, "status block");
+    CK(ctx->k1_zero.ensure(z_total));
     CK(ctx->arena.ensure(ctx->arena_want));
-    if (want_lines) {
-        CK(ctx->tile_state.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
-        CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(ctx->tile_state.p, 0, ((size_t)n_tiles + 1) * sizeof(unsigned long long), st));
-    }
-    CK(cudaMemsetAsync(ctx->status.p, 0, sizeof(PileupStatusDev), st));
-    CK(cudaMemsetAsync(ctx->status.p, 0xff, sizeof(unsigned long long), st));     // first_error = ~0
-    CK(cudaMemsetAsync(ctx->site_cells.p, 0, (sites->n_unique + 1) * sizeof(unsigned long long), st));
+    if (want_lines) CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->k1_zero.p, 0, z_total, st));
+    uint8_t *zb = (uint8_t *)ctx->k1_zero.p;
     PileupArgs a;
     a.text = (const uint8_t *)text_dev;
     a.nbytes = nbytes;
@@ -287,12 +286,12 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     memcpy(&a.p, params, sizeof(CallParams));
     a.mode = mode;
     a.n_tiles = n_tiles;
-    a.site_cells = (unsigned long long *)ctx->site_cells.p;
+    a.site_cells = (unsigned long long *)(zb + z_cells);
     a.line_out = want_lines ? line_out_dev : nullptr;
     a.line_out_cap = want_lines ? (unsigned long long)line_out_cap : 0ull;
-    a.tile_state = want_lines ? (unsigned long long *)ctx->tile_state.p : nullptr;
+    a.tile_state = want_lines ? (unsigned long long *)(zb + z_tiles) : nullptr;
     a.tile_first = want_lines ? (unsigned long long *)ctx->tile_first.p : nullptr;
-    a.st = (PileupStatusDev *)ctx->status.p;
+    a.st = (PileupStatusDev *)(zb + z_status);
     a.arena = (uint8_t *)ctx->arena.p;
     a.arena_cap = ctx->arena.cap;
     const int bps = ctx->k1_blocks[params->min_base_qual > 0 ? 1 : 0];
@@ -300,9 +299,7 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
         TimedLaunch t(ctx, SNPGPU_KERNEL_PILEUP);
         ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
     }
-    if (sites->n_snp)
-        ctx->launches += (uint64_t)k1_launch_row(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev);
-    if (stats_dev) ctx->launches += (uint64_t)k1_launch_stats(st, a.st, stats_dev);
+    ctx->launches += (uint64_t)k1_launch_finish(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev, a.st, stats_dev);
     CK(cudaGetLastError());
     return SNPGPU_OK;
 }

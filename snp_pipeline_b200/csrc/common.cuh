@@ -12,7 +12,8 @@ namespace snpgpu {
 // Device-side status of one pileup call.  first_error orders errors by file offset so the one reported is
 // the one the reference would have raised first.
 struct PileupStatusDev {
-    unsigned long long first_error;   // (byte offset of the line << 8) | code ; ~0 when clean (atomicMin)
+    unsigned long long first_error_inv;   // ~((byte offset of the line << 8) | code), 0 when clean (atomicMax): the
+                                          // whole status starts as zeros, like the other per-call scratch
     unsigned long long n_lines;
     unsigned long long n_parsed;
     unsigned long long n_general;

@@ -9,10 +9,9 @@ size_t k1_smem_bytes();
 int    k1_blocks_per_sm(bool has_qual);
 // enqueue the pileup kernel over `a`; returns the number of kernels launched
 int    k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks);
-int    k1_launch_row(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique,
-                     size_t n_snp, uint8_t *row_out_dev);
+int    k1_launch_finish(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique,
+                        size_t n_snp, uint8_t *row_out_dev, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev);
 int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
-int    k1_launch_stats(cudaStream_t stream, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev);
 
 // k2_merge.cu
 // sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller

@@ -77,7 +77,7 @@ struct K1Cold {
 };
 
 __device__ __forceinline__ void k1_report(const PileupArgs &a, unsigned long long goff, int code) {
-    atomicMin(&a.st->first_error, (goff << 8) | (unsigned long long)code);
+    atomicMax(&a.st->first_error_inv, ~((goff << 8) | (unsigned long long)code));
 }
 
 // call_consensus.py:165-176: Region failure, '-' substitution, keep the cell for the snplist gather.
@@ -595,30 +595,32 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     }
 }
 
-// ---- K3: gather the site cells into the consensus row, snplist order (call_consensus.py:187-188) ---------
-__global__ void k1_row_kernel(const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
-                              uint8_t *row_out) {
+// ---- K3: gather the site cells into the consensus row, snplist order (call_consensus.py:187-188); the first
+//      thread also turns the device-side status into the caller's snpgpu_pileup_stats ----------------------
+__global__ void k1_finish_kernel(const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
+                                 uint8_t *row_out, const PileupStatusDev *st, snpgpu_pileup_stats *out) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_snp) return;
-    unsigned long long c = site_cells[snp_unique[k]];
-    row_out[k] = c ? (uint8_t)(c & 0xffu) : (uint8_t)'-';
-}
-
-__global__ void k1_stats_kernel(const PileupStatusDev *st, snpgpu_pileup_stats *out) {
-    out->n_lines = st->n_lines;
-    out->n_parsed = st->n_parsed;
-    out->n_general = st->n_general;
-    if (st->arena_overflow) {
-        out->error_offset = st->arena_used;                   // bytes of scratch the call needs
-        out->error_code = SNPGPU_E_NOMEM;
-    } else if (st->first_error != ~0ull) {
-        out->error_offset = st->first_error >> 8;
-        out->error_code = (int32_t)(st->first_error & 0xffull);
-    } else {
-        out->error_offset = ~0ull;
-        out->error_code = 0;
+    if (k < n_snp) {
+        unsigned long long c = site_cells[snp_unique[k]];
+        row_out[k] = c ? (uint8_t)(c & 0xffu) : (uint8_t)'-';
     }
-    out->reserved = 0;
+    if (k == 0 && out) {
+        out->n_lines = st->n_lines;
+        out->n_parsed = st->n_parsed;
+        out->n_general = st->n_general;
+        if (st->arena_overflow) {
+            out->error_offset = st->arena_used;               // bytes of scratch the call needs
+            out->error_code = SNPGPU_E_NOMEM;
+        } else if (st->first_error_inv != 0ull) {
+            const unsigned long long e = ~st->first_error_inv;
+            out->error_offset = e >> 8;
+            out->error_code = (int32_t)(e & 0xffull);
+        } else {
+            out->error_offset = ~0ull;
+            out->error_code = 0;
+        }
+        out->reserved = 0;
+    }
 }
 
 // universal newlines (pileup.py:417): a CR that is not followed by LF ends a line -> make it an LF, in place
@@ -663,15 +665,11 @@ int k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks) {
     return 1;
 }
 
-int k1_launch_row(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
-                  uint8_t *row_out_dev) {
-    if (!n_snp) return 0;
-    k1_row_kernel<<<(unsigned)((n_snp + 255) / 256), 256, 0, stream>>>(site_cells, snp_unique, n_snp, row_out_dev);
-    return 1;
-}
-
-int k1_launch_stats(cudaStream_t stream, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev) {
-    k1_stats_kernel<<<1, 1, 0, stream>>>(st, stats_dev);
+int k1_launch_finish(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
+                     uint8_t *row_out_dev, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev) {
+    if (!n_snp && !stats_dev) return 0;
+    const unsigned grid = (unsigned)((n_snp + 255) / 256);
+    k1_finish_kernel<<<grid ? grid : 1u, 256, 0, stream>>>(site_cells, snp_unique, n_snp, row_out_dev, st, stats_dev);
     return 1;
 }
 
