@@ -133,6 +133,44 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
                                 uint8_t *row_out_dev, uint16_t *line_out_dev, size_t line_out_cap,
                                 snpgpu_pileup_stats *stats_dev);
 
+/* ---- K5: per-line tallies for the per-sample consensus VCF.  Replaces what
+ *      vcf_writer.SingleSampleWriter._make_vcf_record_from_pileup (vcf_writer.py:295-379) reads off each
+ *      pileup.Record that call_consensus.py:161-184 hands it: one record per pileup line that K1 parsed (lines at
+ *      snplist / exclude positions in SNPGPU_MODE_SITES, every line in SNPGPU_MODE_ALL), in file order.
+ *      ALT alleles are every surviving symbol other than REF.upper(), in most_common_good_bases order
+ *      (pileup.py:260-266); a record's alleles are alt_out[alt_index .. alt_index + n_alt).
+ *      Must follow a successful snpgpu_pileup_consensus() on the same context with the same sites / params /
+ *      mode: it works on the device copy of that call's text.  When a capacity is too small the call returns
+ *      SNPGPU_E_NOMEM with *n_rec / *n_alt set to what is needed. ------------------------------------------ */
+#define SNPGPU_VCF_HAS_DEPTH     1   /* most_common_good_bases is not None                   */
+#define SNPGPU_VCF_FIRST_IS_REF  2   /* most_common_good_bases[0] == REF.upper()             */
+
+typedef struct {
+    uint64_t offset;       /* byte offset of the pileup line                                  */
+    int64_t  pos;          /* column 2                                                        */
+    int64_t  raw_depth;    /* column 4 (SDP)                                                  */
+    uint64_t alt_index;    /* first ALT entry of this record in alt_out                       */
+    uint32_t chrom_off;    /* column 1 is text[offset + chrom_off .. + chrom_len)             */
+    uint32_t chrom_len;
+    int32_t  contig;       /* index of column 1 in the site table's contig names, or -1       */
+    uint32_t rd, rdf, rdr; /* good depth of REF.upper(): total, forward, reverse              */
+    uint32_t n_alt;
+    uint8_t  ref;          /* column 3 as written                                             */
+    uint8_t  cons;         /* consensus base (pileup.py:586-588), '-' without good depth      */
+    uint8_t  fail;         /* SNPGPU_FAIL_* mask, Region included                             */
+    uint8_t  flags;        /* SNPGPU_VCF_*                                                    */
+} snpgpu_vcf_record;
+
+typedef struct {
+    uint32_t ad, adf, adr; /* good depth of the allele: total, forward, reverse               */
+    uint8_t  base;         /* the allele (upper-cased symbol)                                 */
+    uint8_t  pad[3];
+} snpgpu_vcf_alt;
+
+int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                              snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec,
+                              snpgpu_vcf_alt *alt_out, size_t alt_cap, size_t *n_alt);
+
 /* Rewrites every CR that is not followed by LF to LF, in place (byte offsets and line structure under
  * universal newlines are unchanged).  Needed only after SNPGPU_E_LONECR. */
 int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes);

@@ -194,6 +194,59 @@ def pileup_consensus(text, snp_list, excluded, params: Params, parse_all=False, 
     return row_b
 
 
+# ----------------------------------------------------------------------------- per-sample consensus VCF
+VCF_FORMAT_STR = "GT:SDP:RD:AD:RDF:RDR:ADF:ADR:FT"
+
+
+def vcf_record_fields(rep: dict, fail_list, failed_snp_gt=".", preserve_ref_case=False):
+    """vcf_writer.py:295-379 (_make_vcf_record_from_pileup) on one line_report(): the values of the VCF columns
+    REF, ALT, FILTER and of the sample column, as PyVCF3 1.0.3's Writer prints them (vcf/parser.py: missing -> '.',
+    empty FILTER list -> 'PASS', lists comma-joined)."""
+    ref = rep["ref"]
+    upper_ref = ref.upper()
+    if not preserve_ref_case:
+        ref = upper_ref
+    common = rep["most_common"]
+    if common is None:
+        alt, gt, ad, adf, adr = [], ".", "0", "0", "0"
+    else:
+        alt = [b for b in common if b != upper_ref]
+        if not alt:
+            gt, ad, adf, adr = "0", "0", "0", "0"
+        else:
+            gt = "0" if common[0] == upper_ref else "1"
+            ad = ",".join(str(rep["total"].get(b, 0)) for b in alt)
+            adf = ",".join(str(rep["fwd"].get(b, 0)) for b in alt)
+            adr = ",".join(str(rep["rev"].get(b, 0)) for b in alt)
+        if fail_list:
+            gt = "." if failed_snp_gt == "." else ("0" if failed_snp_gt == "0" else "1")
+    ft = ";".join(fail_list) if fail_list else "PASS"
+    sample = ":".join([gt, str(rep["raw_depth"]), str(rep["total"].get(upper_ref, 0)), ad,
+                       str(rep["fwd"].get(upper_ref, 0)), str(rep["rev"].get(upper_ref, 0)), adf, adr, ft])
+    return ref, (",".join(alt) if alt else "."), ft, sample
+
+
+def consensus_vcf_body(text: bytes, snp_list, excluded, params: Params, parse_all=False, failed_snp_gt=".",
+                       preserve_ref_case=False) -> str:
+    """The data lines of the consensus VCF call_consensus.py:161-184 writes: one per pileup line the Reader yields
+    (pileup.py:408-429), in file order.  Pure-Python driver over line_report(): small inputs only."""
+    wanted = None if parse_all else (set(snp_list) | set(excluded))
+    excluded = set(excluded)
+    out = []
+    for line in text.decode("ascii").splitlines():          # universal newlines, like open() in text mode
+        cols = line.rstrip().split()
+        if wanted is not None:
+            if (cols[0], int(cols[1])) not in wanted:
+                continue
+        rep = line_report(line.encode(), params)
+        if rep["status"]:
+            raise OracleError(rep["status"], 0)
+        mask = rep["fail"] | (FAIL_REGION if (cols[0], rep["pos"]) in excluded else 0)
+        ref, alt, ft, sample = vcf_record_fields(rep, fail_names(mask, params), failed_snp_gt, preserve_ref_case)
+        out.append("\t".join([cols[0], str(rep["pos"]), ".", ref, alt, ".", ft, "NS=1", VCF_FORMAT_STR, sample]) + "\n")
+    return "".join(out)
+
+
 # ----------------------------------------------------------------------------- file formats
 _ROW_SPLIT = re.compile("\t| +")
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_enable_timing",
     "snpgpu_kernel_time", "snpgpu_sites_create",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
-    "snpgpu_normalize_newlines_dev",
+    "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
 ]
@@ -39,6 +39,17 @@ class Params(ctypes.Structure):
 class PileupStats(ctypes.Structure):
     _fields_ = [("n_lines", ctypes.c_uint64), ("n_parsed", ctypes.c_uint64), ("n_general", ctypes.c_uint64),
                 ("error_offset", ctypes.c_uint64), ("error_code", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+VCF_HAS_DEPTH, VCF_FIRST_IS_REF = 1, 2
+
+# snpgpu_vcf_record / snpgpu_vcf_alt (include/snpgpu.h) as numpy record layouts
+VCF_RECORD_DTYPE = np.dtype([("offset", "<u8"), ("pos", "<i8"), ("raw_depth", "<i8"), ("alt_index", "<u8"),
+                             ("chrom_off", "<u4"), ("chrom_len", "<u4"), ("contig", "<i4"), ("rd", "<u4"),
+                             ("rdf", "<u4"), ("rdr", "<u4"), ("n_alt", "<u4"), ("ref", "u1"), ("cons", "u1"),
+                             ("fail", "u1"), ("flags", "u1")])
+VCF_ALT_DTYPE = np.dtype([("ad", "<u4"), ("adf", "<u4"), ("adr", "<u4"), ("base", "u1"), ("pad", "u1", (3,))])
+assert VCF_RECORD_DTYPE.itemsize == 64 and VCF_ALT_DTYPE.itemsize == 16
 
 
 class SynthSpec(ctypes.Structure):
@@ -110,6 +121,8 @@ def load():
     L.snpgpu_pileup_consensus_dev.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, vp]
     L.snpgpu_normalize_newlines_dev.restype = ctypes.c_int
     L.snpgpu_normalize_newlines_dev.argtypes = [vp, vp, sz]
+    L.snpgpu_pileup_vcf_records.restype = ctypes.c_int
+    L.snpgpu_pileup_vcf_records.argtypes = [vp, vp, P(Params), ctypes.c_int, vp, sz, P(sz), vp, sz, P(sz)]
     L.snpgpu_merge_sites.restype = ctypes.c_int
     L.snpgpu_merge_sites.argtypes = [vp, vp, vp, sz, vp, vp, vp, P(sz)]
     L.snpgpu_merge_sites_dev.restype = ctypes.c_int
@@ -274,6 +287,25 @@ class Context(object):
         if lines is not None:
             return out_row, stats, lines[:stats.n_lines]
         return out_row, stats
+
+    def pileup_vcf_records(self, sites, params, mode=MODE_SITES):
+        """K5: the tallies behind the consensus VCF, one record per pileup line that the preceding pileup_consensus()
+        call parsed (same sites / params / mode), in file order.  Returns (records, alts) as numpy record arrays
+        (VCF_RECORD_DTYPE, VCF_ALT_DTYPE); a record's ALT alleles are alts[alt_index : alt_index + n_alt]."""
+        rec_cap, alt_cap = 4 * sites.n_snp + 1024, 8 * sites.n_snp + 2048
+        for _ in range(3):
+            rec = np.zeros(rec_cap, dtype=VCF_RECORD_DTYPE)
+            alt = np.zeros(alt_cap, dtype=VCF_ALT_DTYPE)
+            n_rec, n_alt = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            rc = self.lib.snpgpu_pileup_vcf_records(self.handle, sites.handle, ctypes.byref(params), mode, _np_ptr(rec),
+                                                    rec_cap, ctypes.byref(n_rec), _np_ptr(alt), alt_cap,
+                                                    ctypes.byref(n_alt))
+            if rc == E_NOMEM and (n_rec.value > rec_cap or n_alt.value > alt_cap):
+                rec_cap, alt_cap = max(rec_cap, n_rec.value), max(alt_cap, n_alt.value)
+                continue
+            self._check(rc)
+            return rec[:n_rec.value], alt[:n_alt.value]
+        raise SnpGpuError(E_NOMEM, "pileup_vcf_records: capacities kept growing")
 
     def pileup_consensus_dev(self, text_ptr, nbytes, sites, params, mode, row_ptr, line_ptr=0, line_cap=0,
                              stats_ptr=0):

@@ -1,15 +1,16 @@
 """`call_consensus` subcommand: consensus base of one sample at the snplist positions -> consensus.fasta.
 
 Mirror of snppipeline/call_consensus.py:18-192 (same Namespace fields, files, messages and error protocol); the
-per-line work (pileup parse, tally, filters, call, gather in snplist order) runs in kernel K1/K3 on the GPU.
+per-line work (pileup parse, tally, filters, call, gather in snplist order) runs in kernel K1/K3 on the GPU, the
+tallies of the optional consensus VCF (--vcfFileName) in K5.
 """
 from __future__ import annotations
 
 import os
-import sys
 
 from . import pileup
 from . import utils
+from . import vcf_writer
 
 
 def call_consensus(args):
@@ -58,13 +59,21 @@ def call_consensus(args):
     else:
         parse_positions = set(snp_list).union(excluded_positions)
     reader = pileup.Reader(all_pileup_file_path, args.minBaseQual, parse_positions)
+    writer = None
     if vcf_file_name:
-        # The per-sample consensus.vcf (vcf_writer.py) is the next row of the scope table and is
-        # not produced by this build; say so rather than write something else.
-        print("Warning: --vcfFileName %s ignored: consensus VCF output is not implemented in snp_pipeline_b200 yet."
-              % vcf_file_name, file=sys.stderr)
+        consensus_file_dir = os.path.dirname(os.path.abspath(consensus_file_path))
+        vcf_file_path = os.path.join(consensus_file_dir, vcf_file_name)
+        writer = vcf_writer.SingleSampleWriter(vcf_file_path, getattr(args, "vcfPreserveRefCase", False))
+        filters = caller.get_filter_descriptions()
+        filters.append(("Region", "Position is in dense region of snps or near the end of the contig."))
+        writer.write_header(sample_name, filters, getattr(args, "vcfRefName", "Unknown reference"))
 
-    consensus_str, stats = reader.call_consensus(caller, snp_list, excluded_positions)
+    try:
+        consensus_str, stats = reader.call_consensus(caller, snp_list, excluded_positions, vcf_writer=writer,
+                                                     failed_snp_gt=getattr(args, "vcfFailedSnpGt", "."))
+    finally:
+        if writer:
+            writer.close()
     utils.verbose_print("parsed pileup lines = %i of %i" % (stats.n_parsed, stats.n_lines))
 
     with open(consensus_file_path, "w") as fasta_file_object:

@@ -41,6 +41,9 @@ struct snpgpu_ctx {
     std::string  err;
     DevBuf k1_zero, tile_first, arena, stats;   // k1_zero: status | tile_state | site_cells, cleared by one memset per call
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
+    size_t text_nbytes = 0;                   // bytes of the last text snpgpu_pileup_consensus() staged ...
+    bool   text_valid = false;                // ... still there (snpgpu_pileup_vcf_records works on it)
+    DevBuf rec_off, rec_sorted, rec_out, alt_out, k5_tmp, k5_state;
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
     DevBuf synth_tmp, synth_n;
@@ -122,7 +125,8 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->arena,
-                     &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
+                     &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
+                     &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
                      &ctx->synth_tmp, &ctx->synth_n};
     for (DevBuf *b : all) b->release();
@@ -257,9 +261,10 @@ void snpgpu_sites_destroy(snpgpu_sites *sites) {
 size_t snpgpu_sites_n_snp(const snpgpu_sites *sites) { return sites ? sites->n_snp : 0; }
 
 // ------------------------------------------------------------------------------------------ K1
-int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
-                                const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,
-                                size_t line_out_cap, snpgpu_pileup_stats *stats_dev) {
+static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
+                  const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,
+                  size_t line_out_cap, snpgpu_pileup_stats *stats_dev, unsigned long long *rec_off,
+                  unsigned long long *rec_count, size_t rec_cap) {
     if (!ctx || !sites || !params || (nbytes && !text_dev)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null argument");
     if (mode != SNPGPU_MODE_SITES && mode != SNPGPU_MODE_ALL) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: bad mode");
     if (((uintptr_t)text_dev & 15u) != 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text must be 16-byte aligned");
@@ -292,6 +297,7 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     a.tile_state = want_lines ? (unsigned long long *)(zb + z_tiles) : nullptr;
     a.tile_first = want_lines ? (unsigned long long *)ctx->tile_first.p : nullptr;
     a.st = (PileupStatusDev *)(zb + z_status);
+    a.rec_off = rec_off; a.rec_count = rec_count; a.rec_cap = rec_cap;
     a.arena = (uint8_t *)ctx->arena.p;
     a.arena_cap = ctx->arena.cap;
     const int bps = ctx->k1_blocks[params->min_base_qual > 0 ? 1 : 0];
@@ -304,6 +310,13 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
     return SNPGPU_OK;
 }
 
+int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
+                                const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,
+                                size_t line_out_cap, snpgpu_pileup_stats *stats_dev) {
+    return k1_run(ctx, text_dev, nbytes, sites, params, mode, row_out_dev, line_out_dev, line_out_cap, stats_dev, nullptr,
+                  nullptr, 0);
+}
+
 int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, const snpgpu_sites *sites,
                             const snpgpu_params *params, int mode, uint8_t *row_out, uint16_t *line_out,
                             size_t line_out_cap, snpgpu_pileup_stats *stats) {
@@ -313,6 +326,7 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
     cudaStream_t st = ctx->stream;
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
     bool normalized = false, skip_copy = false;
+    ctx->text_valid = false;
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(ctx->text.ensure(nbytes + 64));
         CK(ctx->row.ensure(sites->n_snp + 16));
@@ -343,6 +357,8 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
             if (n) CK(cudaMemcpy(line_out, ctx->lines.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
         }
         if (stats) *stats = hs;
+        ctx->text_nbytes = nbytes;
+        ctx->text_valid = hs.error_code == 0;
         if (hs.error_code) {
             char msg[160];
             snprintf(msg, sizeof msg, "pileup_consensus: the reference raises (code %d) on the line at byte offset %llu",
@@ -352,6 +368,85 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
         return SNPGPU_OK;
     }
     return fail(ctx, SNPGPU_E_NOMEM, "pileup_consensus: splice scratch");
+}
+
+// ------------------------------------------------------------------------------------------ K5
+int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                              snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec, snpgpu_vcf_alt *alt_out,
+                              size_t alt_cap, size_t *n_alt) {
+    if (!ctx || !sites || !params || !n_rec || !n_alt) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null argument");
+    if (!ctx->text_valid) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: no staged text (call snpgpu_pileup_consensus first)");
+    if ((rec_cap && !rec_out) || (alt_cap && !alt_out)) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null output");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nbytes = ctx->text_nbytes;
+    // state block: [0] lines listed by K1, [1] ALT entries claimed, then the tally kernel's status
+    CK(ctx->k5_state.ensure(256 + sizeof(PileupStatusDev)));
+    unsigned long long *counts = (unsigned long long *)ctx->k5_state.p;
+    PileupStatusDev *k5st = (PileupStatusDev *)((uint8_t *)ctx->k5_state.p + 256);
+    CK(ctx->row.ensure(sites->n_snp + 16));
+    // ---- which lines did K1 parse?  run it again with the list switched on (the list may have to grow once)
+    size_t guess = mode == SNPGPU_MODE_ALL ? nbytes / 8 + 16 : 4 * sites->n_unique + 1024;
+    unsigned long long listed = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->rec_off.ensure(guess * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->k5_state.p, 0, 256 + sizeof(PileupStatusDev), st));
+        int rc = k1_run(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p, nullptr, 0, nullptr,
+                        (unsigned long long *)ctx->rec_off.p, counts, guess);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&listed, counts, sizeof(listed), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (listed <= guess) break;
+        guess = (size_t)listed;
+        if (attempt == 1) return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: line list kept growing");
+    }
+    const size_t n = (size_t)listed;
+    *n_rec = n;
+    *n_alt = 0;
+    if (n == 0) return SNPGPU_OK;
+    // ---- file order
+    const size_t sort_b = k5_sort_bytes(n);
+    CK(ctx->k5_tmp.ensure(sort_b + 256));
+    CK(ctx->rec_sorted.ensure(n * sizeof(unsigned long long)));
+    if (k5_sort_offsets(st, (const unsigned long long *)ctx->rec_off.p, (unsigned long long *)ctx->rec_sorted.p, n,
+                        ctx->k5_tmp.p, ctx->k5_tmp.cap))
+        return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: sort failed");
+    ctx->launches += 4;
+    // ---- tallies; ALT entries are claimed with a counter, so the device buffer may have to grow once as well
+    CK(ctx->rec_out.ensure(n * sizeof(snpgpu_vcf_record)));
+    size_t alt_room = std::max<size_t>(alt_cap, 2 * n + 64);
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CK(ctx->alt_out.ensure(alt_room * sizeof(snpgpu_vcf_alt)));
+        CK(ctx->arena.ensure(ctx->arena_want));
+        CK(cudaMemsetAsync((uint8_t *)ctx->k5_state.p + 8, 0, 248 + sizeof(PileupStatusDev), st));
+        ctx->launches += (uint64_t)k5_launch_tally(st, (const uint8_t *)ctx->text.p, nbytes, sites->table,
+                                                   *reinterpret_cast<const CallParams *>(params),
+                                                   (const unsigned long long *)ctx->rec_sorted.p, n,
+                                                   (snpgpu_vcf_record *)ctx->rec_out.p, (snpgpu_vcf_alt *)ctx->alt_out.p,
+                                                   alt_room, counts + 1, k5st, (uint8_t *)ctx->arena.p, ctx->arena.cap);
+        CK(cudaGetLastError());
+        unsigned long long claimed = 0;
+        PileupStatusDev hst;
+        CK(cudaMemcpyAsync(&claimed, counts + 1, sizeof(claimed), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&hst, k5st, sizeof(hst), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hst.arena_overflow) { ctx->arena_want = (size_t)hst.arena_used + (1 << 20); continue; }
+        if (hst.first_error_inv) {
+            const unsigned long long e = ~hst.first_error_inv;
+            char msg[160];
+            snprintf(msg, sizeof msg, "pileup_vcf_records: the reference raises (code %d) on the line at byte offset %llu",
+                     (int)(e & 0xff), (unsigned long long)(e >> 8));
+            return fail(ctx, (int)(e & 0xff), msg);
+        }
+        if (claimed > alt_room) { alt_room = (size_t)claimed; continue; }
+        *n_alt = (size_t)claimed;
+        if (n > rec_cap || claimed > alt_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: output capacity too small");
+        CK(cudaMemcpyAsync(rec_out, ctx->rec_out.p, n * sizeof(snpgpu_vcf_record), cudaMemcpyDeviceToHost, st));
+        if (claimed) CK(cudaMemcpyAsync(alt_out, ctx->alt_out.p, (size_t)claimed * sizeof(snpgpu_vcf_alt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SNPGPU_OK;
+    }
+    return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: scratch kept growing");
 }
 
 int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes) {

@@ -52,6 +52,9 @@ struct PileupArgs {
     unsigned long long  line_out_cap;
     unsigned long long *tile_state;    // [n_tiles], zero-initialised: decoupled look-back over the tiles' line counts
     unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (set by the warp that owns it)
+    unsigned long long *rec_off;       // null, or: file offset of every parsed line is appended here (any order) ...
+    unsigned long long *rec_count;     // ... through this counter (the consensus-VCF pass, k5_vcf.cu)
+    unsigned long long  rec_cap;
     PileupStatusDev    *st;
     uint8_t            *arena;
     unsigned long long  arena_cap;

@@ -9,7 +9,7 @@
 
 #if defined(__CUDACC__)
 #define SNP_HD __host__ __device__ __forceinline__
-#define SNP_HD_NOINLINE __host__ __device__ __noinline__
+#define SNP_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define SNP_HD inline
 #define SNP_HD_NOINLINE inline

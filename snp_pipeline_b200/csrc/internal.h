@@ -13,6 +13,14 @@ int    k1_launch_finish(cudaStream_t stream, const unsigned long long *site_cell
                         size_t n_snp, uint8_t *row_out_dev, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev);
 int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
 
+// k5_vcf.cu
+size_t k5_sort_bytes(size_t n);
+int    k5_sort_offsets(cudaStream_t stream, const unsigned long long *in, unsigned long long *out, size_t n, void *tmp,
+                       size_t tmp_bytes);
+int    k5_launch_tally(cudaStream_t stream, const uint8_t *text, size_t nbytes, const SiteTable &sites, const CallParams &p,
+                       const unsigned long long *offsets, size_t n_rec, snpgpu_vcf_record *rec_out, snpgpu_vcf_alt *alt_out,
+                       size_t alt_cap, unsigned long long *alt_count, PileupStatusDev *st, uint8_t *arena, size_t arena_cap);
+
 // k2_merge.cu
 // sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller
 size_t k2_workspace_bytes(size_t n);

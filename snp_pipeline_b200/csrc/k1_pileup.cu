@@ -88,6 +88,10 @@ __device__ __forceinline__ uint16_t k1_cell(const PileupArgs &a, unsigned base_c
     if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
     unsigned cell = (fail || base_ch == '*') ? (unsigned)'-' : base_ch;
     if (flags & SITE_SNP) atomicMax(&a.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
+    if (a.rec_off) {                                          // the VCF pass wants to know which lines were parsed
+        const unsigned long long k = atomicAdd(a.rec_count, 1ull);
+        if (k < a.rec_cap) a.rec_off[k] = goff;
+    }
     return (uint16_t)(cell | (fail << 8));
 }
 

@@ -258,4 +258,96 @@ SNP_HD_NOINLINE void general_line(const uint8_t *line, int64_t n, const CallPara
     r->base = (uint8_t)((w == U) ? r->ref : w);                // pileup.py:586-588
 }
 
+// ---- full tallies of one line, for the per-sample consensus VCF (vcf_writer.py:295-379) ----------------------
+// What pileup.Record exposes to SingleSampleWriter._make_vcf_record_from_pileup: raw depth, the reference base's
+// depths, and every other symbol that survived -- the ALT alleles -- with total / forward / reverse depth, in
+// most_common_good_bases order (pileup.py:260-266: count descending, then byte ascending).
+struct LineTallyOut {
+    int      status;        // ST_OK, ST_VALUE/INDEX/UNPACK/DOMAIN, or ST_NEED_ARENA
+    int64_t  pos, raw_depth;
+    int64_t  chrom_off, chrom_len;
+    int64_t  bases_len;
+    uint8_t  ref, base, fail;
+    uint8_t  has_depth;     // 0: most_common_good_bases is None (no good depth)
+    uint8_t  first_is_ref;  // most_common_good_bases[0] == REF.upper()
+    uint32_t rd, rdf, rdr;  // base_good_depth / forward / reverse of REF.upper()
+    uint32_t n_alt;
+};
+
+// pass: totals, forward and reverse counts per upper-cased symbol (pileup.py:259, 269-274)
+struct FullSink {
+    const uint8_t *q; int64_t nq; int thr; unsigned U, L;
+    uint32_t *total, *fwd, *rev; uint32_t good;
+    SNP_HD bool operator()(unsigned c, int64_t k) {
+        if (k >= nq) return false;
+        if ((int)q[k] < thr) return true;
+        if (c == '.') c = U;
+        if (c == ',') c = L;
+        total[up8(c) & 127]++;
+        if (c <= 'Z') fwd[c & 127]++;
+        if (c >= 'a') rev[up8(c) & 127]++;
+        good++;
+        return true;
+    }
+};
+
+// tot/fwd/rev: caller-provided arrays of 128 counters each; on return they hold the per-symbol depths, from which
+// the caller lists the n_alt ALT alleles with next_alt().
+SNP_HD_NOINLINE void general_tally(const uint8_t *line, int64_t n, const CallParams &p, uint8_t *scratch,
+                                   int64_t scratch_len, uint32_t *tot, uint32_t *fwd, uint32_t *rev, LineTallyOut *r) {
+    r->status = ST_OK; r->pos = 0; r->raw_depth = 0; r->ref = 0; r->base = '-'; r->fail = FAIL_RAWDPTH; r->bases_len = 0;
+    r->has_depth = 0; r->first_is_ref = 0; r->rd = r->rdf = r->rdr = 0; r->n_alt = 0; r->chrom_off = r->chrom_len = 0;
+    for (int64_t i = 0; i < n; i++) if (line[i] >= 0x80) { r->status = ST_DOMAIN; return; }
+    Tok t[6];
+    int nt = split_tokens(line, n, t, 6);
+    if (nt < 2) { r->status = ST_INDEX; return; }
+    r->chrom_off = t[0].off; r->chrom_len = t[0].len;
+    int st = py_int(line + t[1].off, t[1].len, &r->pos);
+    if (st) { r->status = st; return; }
+    if (nt < 4) { r->status = ST_INDEX; return; }
+    st = py_int(line + t[3].off, t[3].len, &r->raw_depth);
+    if (st) { r->status = st; return; }
+    if (t[2].len != 1) { r->status = ST_DOMAIN; return; }
+    r->ref = line[t[2].off];
+    if (r->raw_depth == 0 || nt < 5) return;                  // empty record (pileup.py:226-234)
+    if (nt < 6) { r->status = ST_INDEX; return; }
+    const uint8_t *b = line + t[4].off;
+    const int64_t m = t[4].len;
+    r->bases_len = m;
+    const unsigned U = up8(r->ref), L = low8(r->ref);
+    for (int i = 0; i < 128; i++) { tot[i] = 0; fwd[i] = 0; rev[i] = 0; }
+    FullSink s{line + t[5].off, t[5].len, 33 + p.min_base_qual, U, L, tot, fwd, rev, 0};
+    if (!walk_streaming(b, m, s)) {
+        if (!scratch || scratch_len < m) { r->status = ST_NEED_ARENA; return; }
+        for (int i = 0; i < 128; i++) { tot[i] = 0; fwd[i] = 0; rev[i] = 0; }
+        s.good = 0;
+        int64_t sb = 0, se = 0;
+        splice_exact(b, m, scratch, &sb, &se);
+        walk_stripped(scratch, sb, se, s);
+    }
+    if (s.good < 1) return;
+    r->has_depth = 1;
+    unsigned w = 0;
+    uint32_t best = 0;
+    for (unsigned c = 0; c < 128; c++) if (tot[c] > best) { best = tot[c]; w = c; }
+    r->fail = filter_mask(s.good, best, fwd[w], rev[w], p);
+    r->base = (uint8_t)((w == U) ? r->ref : w);
+    r->first_is_ref = w == U;
+    r->rd = tot[U & 127]; r->rdf = fwd[U & 127]; r->rdr = rev[U & 127];
+    uint32_t na = 0;
+    for (unsigned c = 0; c < 128; c++) if (c != (U & 127u) && tot[c] > 0) na++;
+    r->n_alt = na;
+}
+
+// The next ALT allele in most_common_good_bases order (count descending, byte ascending) among the symbols other
+// than REF.upper() whose total is still non-zero; zeroes that total so that repeated calls walk the list.
+SNP_HD unsigned next_alt(uint32_t *tot, unsigned ref_upper, uint32_t *count) {
+    unsigned a = 0;
+    uint32_t bc = 0;
+    for (unsigned c = 0; c < 128; c++) if (c != (ref_upper & 127u) && tot[c] > bc) { bc = tot[c]; a = c; }
+    *count = bc;
+    tot[a] = 0;
+    return a;
+}
+
 }  // namespace snpgpu

@@ -32,7 +32,7 @@ class ConsensusCaller(object):
         return [
             (self.failed_raw_depth_filter, "No read depth"),
             (self.failed_freq_filter, "Variant base frequency below %.2f" % self.min_cons_freq),
-            (self.failed_depth_filter, "Less than %i variant-supporing reads" % self.min_cons_depth),
+            (self.failed_depth_filter, "Less than %i supporting reads" % self.min_cons_depth),
             (self.failed_strand_depth_filter, "Less than %i variant-supporing reads on at least one strand"
              % self.min_cons_strand_depth),
             (self.failed_strand_bias_filter,
@@ -79,18 +79,23 @@ class Reader(object):
                 got += n
         return arr[:got], owner
 
-    def call_consensus(self, caller, snp_list, excluded_positions=()):
+    def call_consensus(self, caller, snp_list, excluded_positions=(), vcf_writer=None, failed_snp_gt='.'):
         """The loop of call_consensus.py:161-188 for this file: returns (consensus string in snp_list order,
         stats).  chrom_position_set None means every line is parsed (--vcfAllPos), otherwise only lines at
         snp_list / excluded positions, exactly like pileup.py:419-429.
+        vcf_writer: an open vcf_writer.SingleSampleWriter (header written) that receives one record per parsed line.
         Raises ValueError / IndexError where the reference does (malformed line at a parsed position)."""
         ctx = device.context()
         sites = ctx.sites(snp_list, excluded_positions)
         text, owner = self.read_text(ctx)
         try:
             mode = _lib.MODE_ALL if self.chrom_position_set is None else _lib.MODE_SITES
+            params = caller.params(self.min_base_quality)
             try:
-                row, stats = ctx.pileup_consensus(text, sites, caller.params(self.min_base_quality), mode)[:2]
+                row, stats = ctx.pileup_consensus(text, sites, params, mode)[:2]
+                if vcf_writer is not None:      # one VCF record per line the reader yields (call_consensus.py:161-184)
+                    records, alts = ctx.pileup_vcf_records(sites, params, mode)
+                    vcf_writer.write_records(text, records, alts, caller, failed_snp_gt)
             except _lib.SnpGpuError as e:
                 raise translate_error(e, self.file_path)
         finally:
