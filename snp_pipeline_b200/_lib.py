@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnpgpu.so")
+LIB_PATH = os.environ.get("SNPGPU_LIB") or os.path.join(_HERE, "libsnpgpu.so")   # (override: tuning builds)
 
 OK, E_VALUE, E_INDEX, E_UNPACK, E_DOMAIN, E_LONECR = 0, 1, 2, 3, 4, 5
 E_CUDA, E_ARG, E_NOMEM, E_LENGTH = 16, 17, 18, 19

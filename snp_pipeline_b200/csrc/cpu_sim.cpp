@@ -40,9 +40,9 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         if (buf[i] == '\r' && buf[i + 1] != '\n') buf[i] = '\n';
     uint64_t n_lines = 0, n_parsed = 0, n_general = 0, n_quick = 0;
     int hint = 0;
-    uint32_t cc_name[16];
+    alignas(16) uint32_t cc_name[16], cc_mask[16];
     ContigCache cc;
-    contig_cache_load(t, hint, cc_name, 16, &cc);
+    contig_cache_load(t, hint, cc_name, cc_mask, 16, &cc);
     size_t s = 0;
     counters[3] = ~0ull; counters[4] = 0;
     std::vector<uint8_t> scratch;
@@ -59,7 +59,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         FastLine fl;
         if (!force_general && !high && p->min_base_qual <= 0) {       // first tier (line_quick.cuh)
             QuickLine q;
-            if (cc.cid != hint) contig_cache_load(t, hint, cc_name, 16, &cc);    // the kernel reloads after a drain
+            if (cc.cid != hint) contig_cache_load(t, hint, cc_name, cc_mask, 16, &cc);    // the kernel reloads after a drain
             st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
             if (st == ST_OK) {
                 if (q.end != e) { counters[3] = s; counters[4] = 99; break; }   // harness self-check: the line end

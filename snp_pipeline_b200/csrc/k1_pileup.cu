@@ -31,12 +31,14 @@ struct K1Warp {                                 // one warp's slice of shared me
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
     uint16_t starts[K1_WCAP];                   // line starts of the current pass, file order: chunk << 5 | flag bit
     uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
-    uint32_t cname[K1_NAMEW];                   // name + tab of the contig the warp expects (ContigCache::name4)
+    alignas(16) uint32_t cname[K1_NAMEW];       // name + tab of the contig the warp expects (ContigCache::name4) ...
+    alignas(16) uint32_t cmask[K1_NAMEW];       // ... and which of its bytes count (ContigCache::mask4)
     unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh:  (line index in its tile << 48) | file offset
     unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
     alignas(8) uint64_t bar;
 };
 
+static_assert(K1_PAD >= (int)QUICK_PAD && K1_NAMEW % 4 == 0, "line_quick.cuh preconditions");
 size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
 
 // exact per-byte mask (0x80 where the byte equals '\n'), any byte values
@@ -114,9 +116,10 @@ __device__ __forceinline__ unsigned long long k1_line_slot(const PileupArgs &a, 
 // yet, 1 the tile's own count, 2 the count of all tiles up to and including it) and the value.
 // k1_tile_publish: tile `tile` owns n lines (right after its scan).  k1_tile_resolve (all 32 lanes): how many lines
 // the earlier tiles own, i.e. the file-order index of this tile's first line; also recorded in tile_first.
-// Every warp publishes its own count before it waits for anybody, tiles are handed out in increasing order and
-// all warps are resident, so the wait always ends; the kernel resolves a tile only after parsing it, when the
-// neighbours have long published, so it rarely waits at all.
+// Tiles are handed out by ticket (PileupStatusDev::next_tile), so every tile in front of a warp's own was taken
+// earlier by a resident warp, which publishes its count right after its scan and before it waits for anybody:
+// the wait always ends.  The kernel resolves a tile only after parsing it, when the tiles in front have long
+// published and most have resolved, so the look-back is usually one round of 32.
 __device__ __forceinline__ void k1_tile_publish(const PileupArgs &a, int tile, uint32_t n) {
     volatile unsigned long long *st = a.tile_state;
     st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n;
@@ -130,14 +133,17 @@ __device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &
         for (int j = tile - 1;; j -= 32) {                    // lane L looks at tile j - L
             const int t = j - lane;
             unsigned long long v = UPTO;                      // in front of tile 0: nothing
-            if (t >= 0) { do { v = st[t]; } while ((v >> 62) == 0ull); }
+            if (t >= 0) {
+                v = st[t];
+                while ((v >> 62) == 0ull) { __nanosleep(100); v = st[t]; }
+            }
             const uint32_t upto = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-            const int stop = upto ? __ffs((int)upto) - 1 : 31;    // nearest tile that knows its running total
-            unsigned long long c = lane <= stop ? (v & VAL) : 0ull;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-            before += c;
-            if (upto) break;
+            const int stop = upto ? __ffs((int)upto) - 1 : 32;    // nearest tile that knows its running total
+            before += (unsigned long long)__reduce_add_sync(0xffffffffu, lane < stop ? (uint32_t)v : 0u);   // own counts < 2^32
+            if (upto) {
+                before += __shfl_sync(0xffffffffu, v & VAL, stop);
+                break;
+            }
         }
         if (lane == 0) st[tile] = UPTO | (before + (unsigned long long)n);
     }
@@ -184,6 +190,20 @@ __device__ __noinline__ void k1_general(const PileupArgs &a, K1Cold &cs, unsigne
     cs.n_parsed++;
 }
 
+// offset from s of the first '\n' in buf[s, s + cap), cap when there is none; buf 4-byte aligned, whole words are
+// read only where all four bytes lie inside the range
+__device__ __forceinline__ uint32_t k1_find_nl(const uint8_t *buf, uint32_t s, uint32_t cap) {
+    uint32_t i = s;
+    const uint32_t end = s + cap;
+    for (; i < end && (i & 3u); i++) if (buf[i] == '\n') return i - s;
+    for (; i + 4u <= end; i += 4u) {
+        const uint32_t m = nl_mask(*reinterpret_cast<const uint32_t *>(buf + i));
+        if (m) return i + ((uint32_t)ctz32(m) >> 3) - s;
+    }
+    for (; i < end; i++) if (buf[i] == '\n') return i - s;
+    return cap;
+}
+
 // second tier: exact tallies (line_fast.cuh) on the text in global memory; returns true when the line has to
 // go on to k1_general().  The words line_fast reads may reach 7 bytes past the line end, so the last lines of
 // the text are left to k1_general(), which reads byte by byte.
@@ -194,8 +214,7 @@ __device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned
     const uint8_t *buf = a.text + abase;
     const uint32_t s = (uint32_t)(goff - abase);
     const uint32_t cap = room < 65536ull ? (uint32_t)room : 65536u;
-    uint32_t n = 0;
-    while (n < cap && buf[s + n] != '\n') n++;
+    const uint32_t n = k1_find_nl(buf, s, cap);
     if (n == cap || (unsigned long long)n + 8ull > room) return true;          // very long, or at the end of the text
     FastLine fl;
     const int st = fast_line<HAS_QUAL>(buf, s, s + n, a.sites, cs.hint, a.p, ALL, &fl);
@@ -356,9 +375,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     K1Cold cs{0, 0u, 0u};
     constexpr bool CHECK_CR = !ALL || HAS_QUAL;
     constexpr uint32_t H = 0x80808080u;
-    const int gwarp = blockIdx.x * K1_WARPS + warp, n_gwarps = gridDim.x * K1_WARPS;
+    const int n_gwarps = gridDim.x * K1_WARPS;
     ContigCache cc;
-    contig_cache_load(a.sites, 0, sm.cname, K1_NAMEW, &cc);   // every lane writes the same words
+    contig_cache_load(a.sites, 0, sm.cname, sm.cmask, K1_NAMEW, &cc);   // every lane writes the same words
     __syncwarp();
     // Per-line results of the tile just parsed wait in shared memory (the tail of lanehits) until the file-order
     // index of the tile's first line is known -- resolved one tile later, while the next window is in flight.
@@ -382,7 +401,14 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         pend_tile = -1;
     };
 
-    for (int tile = gwarp; tile < a.n_tiles; tile += n_gwarps) {
+    int ticket = 0;                                           // lane 0: the next tile, when ticket_taken
+    bool ticket_taken = false;                                // (warp-uniform)
+    for (;;) {
+        // tiles in increasing order (see k1_tile_resolve); usually taken during the last parse step of the tile before
+        if (!ticket_taken && lane == 0) ticket = (int)atomicAdd(&a.st->next_tile, 1u);
+        const int tile = __shfl_sync(0xffffffffu, ticket, 0);
+        ticket_taken = false;
+        if (tile >= a.n_tiles) break;
         {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
             const int hint = cs.hint;
             const uint32_t moved = __ballot_sync(0xffffffffu, hint != cc.cid);
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 const int nh = __shfl_sync(0xffffffffu, hint, 31 - __clz((int)moved));
                 cs.hint = nh;
                 __syncwarp();
-                contig_cache_load(a.sites, nh, sm.cname, K1_NAMEW, &cc);
+                contig_cache_load(a.sites, nh, sm.cname, sm.cmask, K1_NAMEW, &cc);
             }
         }
         const unsigned long long base = (unsigned long long)tile * K1_TILE;
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             fence_proxy_async();
             mbar_arrive_expect_tx(&sm.bar, bulk);
             bulk_g2s(sm.buf, a.text + base, bulk, &sm.bar);
-            const unsigned long long nbase = base + (unsigned long long)n_gwarps * K1_TILE;   // this warp's next tile -> L2
+            const unsigned long long nbase = base + (unsigned long long)n_gwarps * K1_TILE;   // the tile a warp will take about one round from now -> L2
             if (nbase < a.nbytes) {
                 const unsigned long long nleft = a.nbytes - nbase;
                 const uint32_t nb = (nleft < (unsigned long long)(K1_TILE + K1_LOOK) ? (uint32_t)nleft : (uint32_t)(K1_TILE + K1_LOOK)) & ~15u;
@@ -414,6 +440,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         flush_pending();                                      // the previous tile's results, while this window loads
+        if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines too: every tile they belong to is resolved now
+            const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
+            n_dq = r & 0xffffu; n_gq = r >> 16;
+        }
         if (bulk) { mbar_wait(&sm.bar, parity); parity ^= 1u; }
         __syncwarp();
         // ---- scan: every lane lists the line starts of its chunks as it finds them -------------------
@@ -545,6 +575,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 perm[hist[(keys >> (4u * k)) & 15u] + (uint32_t)((ranks >> (8u * k)) & 0xffu)] = (uint8_t)l;
             __syncwarp();
             for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
+                if (l0 + 32u >= n_pass && done + n_pass == n_tile_lines) {   // last step of the tile: the next ticket,
+                    if (lane == 0) ticket = (int)atomicAdd(&a.st->next_tile, 1u);   // its latency hidden behind the parse
+                    ticket_taken = true;
+                }
                 const bool have = l0 + (uint32_t)lane < n_pass;
                 const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
                 const uint32_t line_idx = done + l;

@@ -66,22 +66,80 @@ struct WordReader {
 };
 
 // The contig a warp currently expects, staged where its lanes reach it without a trip to global memory
-// (the name in shared memory, the rest in registers).  len1 == 0: nothing cached, every line is declined.
+// (name and byte masks in shared memory, the rest in registers).  len1 == 0: nothing cached, every line is declined.
+constexpr uint32_t QUICK_PAD = 32;   // '\n' sentinels the caller keeps behind `limit` (word over-reads land there)
+
 struct ContigCache {
-    const uint32_t *name4;     // name bytes + '\t', zero padded to whole words
+    const uint32_t *name4;     // name bytes + '\t', zero padded to blocks of four words (16-byte aligned)
+    const uint32_t *mask4;     // per word: 0xff in the bytes that belong to name + tab
     uint32_t len1;             // name length + 1
+    uint32_t nblk;             // four-word blocks that cover name + tab
     int32_t  cid;              // index in the site table
     int64_t  max_pos;          // largest site position on the contig, -1 when it holds none
     int64_t  bit_base;
 };
 
-SNP_HD void contig_cache_load(const SiteTable &t, int cid, uint32_t *name4_store, uint32_t store_words, ContigCache *cc) {
-    cc->name4 = name4_store; cc->len1 = 0; cc->cid = cid; cc->max_pos = -1; cc->bit_base = 0;
+// name4_store / mask4_store: store_words words each (a multiple of 4), 16-byte aligned
+SNP_HD void contig_cache_load(const SiteTable &t, int cid, uint32_t *name4_store, uint32_t *mask4_store,
+                              uint32_t store_words, ContigCache *cc) {
+    cc->name4 = name4_store; cc->mask4 = mask4_store; cc->len1 = 0; cc->nblk = 0; cc->cid = cid; cc->max_pos = -1;
+    cc->bit_base = 0;
     if (cid < 0 || cid >= t.n_contigs) return;
     const uint32_t L = (uint32_t)t.len1[cid], nw = (L + 3u) >> 2;
     if (nw > store_words) return;
-    for (uint32_t j = 0; j < nw; j++) name4_store[j] = t.names4[t.off4[cid] + j];
-    cc->len1 = L; cc->max_pos = t.max_pos[cid]; cc->bit_base = t.bit_base[cid];
+    for (uint32_t j = 0; j < store_words; j++) {
+        name4_store[j] = j < nw ? t.names4[t.off4[cid] + j] : 0u;
+        mask4_store[j] = 4u * j + 4u <= L ? 0xffffffffu : (4u * j < L ? (1u << (8u * (L - 4u * j))) - 1u : 0u);
+    }
+    cc->len1 = L; cc->nblk = (nw + 3u) >> 2; cc->max_pos = t.max_pos[cid]; cc->bit_base = t.bit_base[cid];
+}
+
+struct Word4 { uint32_t x, y, z, w; };
+SNP_HD Word4 load_word4(const uint32_t *p) {                  // p 16-byte aligned
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    return Word4{v.x, v.y, v.z, v.w};
+#else
+    return Word4{p[0], p[1], p[2], p[3]};
+#endif
+}
+
+// value of four decimal digit bytes (0..9 each, most significant in the lowest byte)
+SNP_HD uint32_t digits4_value(uint32_t w) {
+    const uint32_t p = (w * 10u + (w >> 8)) & 0x00ff00ffu;    // byte 0: d0 d1, byte 2: d2 d3
+    return (p & 0xffffu) * 100u + (p >> 16);
+}
+
+// 1..7 decimal digits at buf[i] (eight or more: fast_digits() takes over); leaves i on the first non-digit.
+// All bytes < 0x80.  Reads the 12 bytes from buf[i & ~3].
+SNP_HD bool quick_digits8(const uint8_t *buf, uint32_t &i, uint32_t &v) {
+    const uint32_t H = 0x80808080u;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(buf + (i & ~3u));
+    const uint32_t sh = (i & 3u) * 8u;
+    const uint32_t a = p[0], b = p[1], c = p[2];
+    const uint32_t lo = funnel_r(a, b, sh) ^ 0x30303030u, hi = funnel_r(b, c, sh) ^ 0x30303030u;   // digits -> 0..9
+    const uint32_t ndl = (lo + 0x76767676u) & H, ndh = (hi + 0x76767676u) & H;                       // bit 7: not a digit
+    if ((ndl | ndh) == 0u) return fast_digits(buf, i, v);
+    const bool in_lo = ndl != 0u;
+    const uint32_t n = in_lo ? (uint32_t)ctz32(ndl) >> 3 : 4u + ((uint32_t)ctz32(ndh) >> 3);
+    const uint32_t s8 = (n & 3u) * 8u;
+    // the digits right-aligned in eight bytes: x_hi = bytes n-4 .. n-1, x_lo = bytes n-8 .. n-5 (zero in front of byte 0)
+    const uint32_t x_hi = funnel_r(in_lo ? 0u : lo, in_lo ? lo : hi, s8);
+    const uint32_t x_lo = in_lo ? 0u : funnel_r(0u, lo, s8);
+    v = digits4_value(x_lo) * 10000u + digits4_value(x_hi);
+    i += n;
+    return n > 0u;
+}
+
+// the same for 1..3 digits (four or more: fast_digits()); reads the 8 bytes from buf[i & ~3]
+SNP_HD bool quick_digits4(const uint8_t *buf, uint32_t &i, uint32_t &v) {
+    const uint32_t w = load_u32(buf, i) ^ 0x30303030u;
+    const uint32_t nd = (w + 0x76767676u) & 0x80808080u;
+    if (nd == 0u) return fast_digits(buf, i, v);
+    const uint32_t n = (uint32_t)ctz32(nd) >> 3;
+    v = digits4_value(funnel_r(0u, w, n * 8u));
+    i += n;
+    return n > 0u;
 }
 
 // One line starting at buf[s]; bytes at and after buf[limit] are '\n' sentinels.  cc: the contig the caller
@@ -91,22 +149,23 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
                       const CallParams &p, bool all_positions, QuickLine *out) {
     const uint32_t H = 0x80808080u, K = 0x7f7f7f7fu;
     // ---- columns 1-4: contig, position, reference base, raw depth ---------------------------------
-    if (cc.len1 == 0) return ST_DETAIL;
-    {
+    if (cc.len1 == 0 || s + 16u * cc.nblk + 8u > limit + QUICK_PAD) return ST_DETAIL;
+    {   // name + tab, four words at a time; bytes behind them are masked out
         const uint32_t *q = reinterpret_cast<const uint32_t *>(buf + (s & ~3u));
-        const uint32_t sh = (s & 3u) * 8u, nw = cc.len1 >> 2, rem = cc.len1 & 3u;
-        uint32_t lo = q[0], diff = 0, j = 0;
-        for (; j < nw; j++) {
-            const uint32_t hi = q[j + 1];
-            diff |= funnel_r(lo, hi, sh) ^ cc.name4[j];
-            lo = hi;
+        const uint32_t sh = (s & 3u) * 8u;
+        uint32_t lo = q[0], diff = 0;
+        for (uint32_t b = 0; b < cc.nblk; b++) {
+            const uint32_t h0 = q[4u * b + 1u], h1 = q[4u * b + 2u], h2 = q[4u * b + 3u], h3 = q[4u * b + 4u];
+            const Word4 nm = load_word4(cc.name4 + 4u * b), mk = load_word4(cc.mask4 + 4u * b);
+            diff |= ((funnel_r(lo, h0, sh) ^ nm.x) & mk.x) | ((funnel_r(h0, h1, sh) ^ nm.y) & mk.y);
+            diff |= ((funnel_r(h1, h2, sh) ^ nm.z) & mk.z) | ((funnel_r(h2, h3, sh) ^ nm.w) & mk.w);
+            lo = h3;
         }
-        if (rem) diff |= (funnel_r(lo, q[j + 1], sh) ^ cc.name4[j]) & ((1u << (8u * rem)) - 1u);
         if (diff) return ST_DETAIL;
     }
     uint32_t i = s + cc.len1;
     uint32_t pos = 0;
-    bool bad = !fast_digits(buf, i, pos);
+    bool bad = !quick_digits8(buf, i, pos);
     bad |= buf[i] != '\t';
     i++;
     if (bad) return ST_DETAIL;
@@ -122,7 +181,7 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     bad |= buf[i + 1] != '\t';
     i += 2;
     uint32_t raw_depth = 0;
-    bad |= !fast_digits(buf, i, raw_depth);
+    bad |= !quick_digits4(buf, i, raw_depth);
     bad |= buf[i] != '\t';
     if (bad || raw_depth == 0) return ST_DETAIL;       // depth 0: pileup.py:226-234, left to the detailed parser
     i++;

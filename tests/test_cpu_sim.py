@@ -117,6 +117,42 @@ def test_nasty_text(sim, seed):
             _compare(sim, text, snps, excl, ps, all_pos)
 
 
+def header_shapes_text(seed):
+    """Contig names of every length 1..45 (all word alignments of the name compare), positions of 1..10 digits
+    (with leading zeros), depths of 1..4 digits: the header columns the first-tier parser reads word-wise."""
+    rng = random.Random(4000 + seed)
+    lines, snps = [], []
+    for k in range(1, 46):
+        chrom = "".join(rng.choice("abcXYZ019|._-") for _ in range(k))
+        for _ in range(6):
+            nd = rng.randint(1, 10)
+            pos = rng.randint(10 ** (nd - 1), 10 ** nd - 1) if nd < 10 else rng.randint(10 ** 9, 2 ** 31 - 1)
+            depth = rng.choice([1, 2, 7, 9, 10, 35, 99, 100, 250, 999, 1000, 1500])
+            ln = linegen.realistic_line(rng, pos, chrom, depth=depth)
+            f = ln.split("\t")
+            if rng.random() < 0.3:
+                f[1] = "0" * rng.randint(1, 3) + f[1]
+            if rng.random() < 0.2 and f[3] != "0":
+                f[3] = "0" + f[3]
+            lines.append("\t".join(f))
+            if rng.random() < 0.6 and pos < 10 ** 7:          # (the site table is a bitmap over positions)
+                snps.append((chrom, pos))
+        if k % 7 == 0:                                   # a neighbour that differs only in its last byte / is a prefix
+            lines.append(linegen.realistic_line(rng, 5, chrom[:-1] + "Q", depth=8))
+            lines.append(linegen.realistic_line(rng, 6, chrom + "x", depth=8))
+            snps += [(chrom[:-1] + "Q", 5), (chrom, 6)]
+    return "".join(lines).encode(), snps
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_header_shapes(sim, seed):
+    text, snps = header_shapes_text(seed)
+    for all_pos in (False, True):
+        c = _compare(sim, text, snps, [], PARAM_SETS[1], all_pos)
+        if all_pos:
+            assert c[5] > c[1] * 0.4, "the first-tier parser should decide many of these lines (%d of %d)" % (c[5], c[1])
+
+
 def _boundary_line(rng, pos):
     """Lines around the first-tier parser's decision boundary (csrc/line_quick.cuh): reference base winning by a
     hair or tied, the reference letter written out, every kind of '^' partner, markers at word boundaries."""

@@ -118,6 +118,23 @@ def test_realistic_text(ctx, seed):
         assert st.n_general < st.n_lines * 0.02 + 5
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_header_shapes(ctx, seed):
+    """Contig names of every length, positions of 1..10 digits, depths of 1..4 digits (the word-wise header parse)."""
+    from test_cpu_sim import header_shapes_text
+    text, snps = header_shapes_text(seed)
+    for all_pos in (False, True):
+        _compare(ctx, text, snps, [], PARAM_SETS[1], all_pos)
+    # one contig over many lines: the first-tier parser takes them
+    rng = random.Random(seed)
+    for chrom in ("c", "chr%d" % seed, "x" * 31, "y" * 32, "NZ_" + "7" * 30, "z" * 63):
+        body = "".join(linegen.realistic_line(rng, 99999990 + k, chrom) for k in range(400))
+        snps1 = [(chrom, 99999990 + k) for k in range(0, 400, 7)]
+        for all_pos in (False, True):
+            st = _compare(ctx, body.encode(), snps1, [], PARAM_SETS[seed % 4], all_pos)
+            assert st.n_general == 0
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_nasty_text(ctx, seed):
     """Legal-but-odd lines (caret chains, odd indel tokens, IUPAC, short quality strings, odd separators, lines the
