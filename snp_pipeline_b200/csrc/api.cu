@@ -269,7 +269,7 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
     if (mode != SNPGPU_MODE_SITES && mode != SNPGPU_MODE_ALL) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: bad mode");
     if (((uintptr_t)text_dev & 15u) != 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text must be 16-byte aligned");
     if (sites->n_snp && !row_out_dev) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: row_out is null");
-    if (nbytes > ((size_t)1 << 45)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text above 32 TiB");
+    if (nbytes >= ((size_t)1 << 38)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text of 256 GiB or more");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);

@@ -33,7 +33,7 @@ struct K1Warp {                                 // one warp's slice of shared me
     uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
     alignas(16) uint32_t cname[K1_NAMEW];       // name + tab of the contig the warp expects (ContigCache::name4) ...
     alignas(16) uint32_t cmask[K1_NAMEW];       // ... and which of its bytes count (ContigCache::mask4)
-    unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh:  (line index in its tile << 48) | file offset
+    unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh (k1_entry)
     unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
     alignas(8) uint64_t bar;
 };
@@ -208,13 +208,14 @@ __device__ __forceinline__ uint32_t k1_find_nl(const uint8_t *buf, uint32_t s, u
 // go on to k1_general().  The words line_fast reads may reach 7 bytes past the line end, so the last lines of
 // the text are left to k1_general(), which reads byte by byte.
 template <bool HAS_QUAL, bool ALL>
-__device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned long long goff, uint32_t line_idx) {
+__device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned long long goff, uint32_t line_idx,
+                                       uint32_t len_hint) {
     const unsigned long long room = a.nbytes - goff;
     const unsigned long long abase = goff & ~15ull;
     const uint8_t *buf = a.text + abase;
     const uint32_t s = (uint32_t)(goff - abase);
     const uint32_t cap = room < 65536ull ? (uint32_t)room : 65536u;
-    const uint32_t n = k1_find_nl(buf, s, cap);
+    const uint32_t n = len_hint && len_hint < cap ? len_hint : k1_find_nl(buf, s, cap);
     if (n == cap || (unsigned long long)n + 8ull > room) return true;          // very long, or at the end of the text
     FastLine fl;
     const int st = fast_line<HAS_QUAL>(buf, s, s + n, a.sites, cs.hint, a.p, ALL, &fl);
@@ -226,6 +227,15 @@ __device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned
 }
 
 // ---- the per-warp queues (all 32 lanes call these together; the fill counts are warp-uniform) -------------
+// entry: line index in its tile << 50 | length hint << 38 | file offset.  The hint is the line's length without its
+// '\n' when the scan's list knows where the next line starts (and it is below 4096), else 0: look for the '\n'.
+static_assert(K1_TILE <= (1 << 14), "queue entries keep a line's index within its tile in 14 bits");
+__device__ __forceinline__ unsigned long long k1_entry(uint32_t line_idx, uint32_t len_hint, unsigned long long goff) {
+    return ((unsigned long long)line_idx << 50) | ((unsigned long long)(len_hint < 4096u ? len_hint : 0u) << 38) | goff;
+}
+__device__ __forceinline__ unsigned long long k1_entry_goff(unsigned long long e) { return e & ((1ull << 38) - 1ull); }
+__device__ __forceinline__ uint32_t k1_entry_len(unsigned long long e) { return (uint32_t)(e >> 38) & 0xfffu; }
+__device__ __forceinline__ uint32_t k1_entry_idx(unsigned long long e) { return (uint32_t)(e >> 50); }
 __device__ __forceinline__ uint32_t k1_push(unsigned long long *q, uint32_t n_q, int lane, bool want,
                                             unsigned long long entry) {
     const uint32_t b = __ballot_sync(0xffffffffu, want);
@@ -245,7 +255,7 @@ __device__ __noinline__ uint32_t k1_drain_general(const PileupArgs &a, K1Warp &s
         const bool mine = (uint32_t)lane < take;
         if (mine) e = sm.gq[n_gq + (uint32_t)lane];
         __syncwarp();
-        if (mine) k1_general(a, cs, e & 0xffffffffffffull, (uint32_t)(e >> 48));
+        if (mine) k1_general(a, cs, k1_entry_goff(e), k1_entry_idx(e));
         __syncwarp();
     }
     return n_gq;
@@ -263,7 +273,7 @@ __device__ __noinline__ uint32_t k1_drain_detail(const PileupArgs &a, K1Warp &sm
         if (mine) e = sm.dq[n_dq + (uint32_t)lane];
         __syncwarp();
         bool more = false;
-        if (mine) more = k1_detail<HAS_QUAL, ALL>(a, cs, e & 0xffffffffffffull, (uint32_t)(e >> 48));
+        if (mine) more = k1_detail<HAS_QUAL, ALL>(a, cs, k1_entry_goff(e), k1_entry_idx(e), k1_entry_len(e));
         __syncwarp();
         n_gq = k1_push(sm.gq, n_gq, lane, more, e);
         n_gq = k1_drain_general(a, sm, cs, lane, n_gq, false);
@@ -306,7 +316,7 @@ __device__ __noinline__ uint32_t k1_slow_tile(const PileupArgs &a, K1Warp &sm, K
                 while (!(sm.buf[cur] == '\n' && cur + 1u < wlen)) cur++;
                 s = ++cur;
             }
-            entry = ((unsigned long long)idx << 48) | (base + s);
+            entry = k1_entry(idx, 0u, base + s);
             idx++; cnt--;
         }
         n_gq = k1_push(sm.gq, n_gq, lane, want, entry);
@@ -402,6 +412,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     };
 
     int ticket = 0;                                           // lane 0: the next tile, when ticket_taken
+    bool drained = false;                                     // queued lines ran since the contig cache was last checked
     bool ticket_taken = false;                                // (warp-uniform)
     for (;;) {
         // tiles in increasing order (see k1_tile_resolve); usually taken during the last parse step of the tile before
@@ -409,7 +420,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         const int tile = __shfl_sync(0xffffffffu, ticket, 0);
         ticket_taken = false;
         if (tile >= a.n_tiles) break;
-        {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
+        if (drained) {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
+            drained = false;
             const int hint = cs.hint;
             const uint32_t moved = __ballot_sync(0xffffffffu, hint != cc.cid);
             if (moved) {
@@ -441,6 +453,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         flush_pending();                                      // the previous tile's results, while this window loads
         if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines too: every tile they belong to is resolved now
+            drained = true;
             const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
             n_dq = r & 0xffffu; n_gq = r >> 16;
         }
@@ -603,9 +616,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         }
                     }
                 }
-                const unsigned long long entry = ((unsigned long long)line_idx << 48) | (base + s);
+                uint32_t len_hint = 0;                        // up to the '\n' in front of the next listed start
+                if (to_detail && l + 1u < n_pass) {
+                    const uint32_t c1 = sm.starts[l + 1u];
+                    len_hint = (c1 >> 5) * 16u + (c1 & 7u) * 4u + ((c1 >> 3) & 3u) - s;
+                }
+                const unsigned long long entry = k1_entry(line_idx, len_hint, base + s);
                 n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
                 if (n_dq >= 32u) {                            // leaves both queues below 32
+                    drained = true;
                     resolve_pending();
                     const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
                     n_dq = r & 0xffffu; n_gq = r >> 16;

@@ -132,7 +132,7 @@ def test_header_shapes(ctx, seed):
         snps1 = [(chrom, 99999990 + k) for k in range(0, 400, 7)]
         for all_pos in (False, True):
             st = _compare(ctx, body.encode(), snps1, [], PARAM_SETS[seed % 4], all_pos)
-            assert st.n_general == 0
+            assert st.n_general <= 1          # (the last line of a text is left to the any-input parser)
 
 
 @pytest.mark.parametrize("seed", range(10))
