@@ -464,19 +464,31 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         uint16_t *myhits = sm.lanehits + lane * K1_LHCAP;
         if (wlen > (uint32_t)K1_TILE) {                       // a whole tile: no chunk needs a bounds test
             uint32_t multi = 0;
+            constexpr int B = 7;                              // chunks loaded together, ahead of the stores below
 #pragma unroll
-            for (int j = 0; j < K1_LANE_CHUNKS; j++) {
-                const uint32_t off = (uint32_t)lane * K1_LANE_BYTES + (uint32_t)j * 16u;
-                const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
-                hi_acc |= v.x | v.y | v.z | v.w;
-                if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
-                const uint32_t NL = 0x0a0a0a0au, K = 0x7f7f7f7fu;
-                const uint32_t x0 = (v.x ^ NL) + K, x1 = (v.y ^ NL) + K, x2 = (v.z ^ NL) + K, x3 = (v.w ^ NL) + K;
-                const uint32_t m = ((~x0 & H) >> 7) | ((~x1 & H) >> 6) | ((~x2 & H) >> 5) | ((~x3 & H) >> 4);
-                const uint32_t code = (((uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j) << 5) | ((uint32_t)__ffs((int)m) - 1u);
-                if (m != 0u && cnt < (uint32_t)K1_LHCAP) myhits[cnt] = (uint16_t)code;   // predicated, no branch
-                cnt += m != 0u ? 1u : 0u;
-                multi |= m & (m - 1u);                        // two starts within 16 bytes
+            for (int j0 = 0; j0 < K1_LANE_CHUNKS; j0 += B) {
+                uint4 vv[B];
+#pragma unroll
+                for (int u = 0; u < B; u++)
+                    if (j0 + u < K1_LANE_CHUNKS)
+                        vv[u] = *reinterpret_cast<const uint4 *>(sm.buf + (uint32_t)lane * K1_LANE_BYTES + (uint32_t)(j0 + u) * 16u);
+#pragma unroll
+                for (int u = 0; u < B; u++) {
+                    if (j0 + u >= K1_LANE_CHUNKS) continue;
+                    const int j = j0 + u;
+                    const uint4 v = vv[u];
+                    hi_acc |= v.x | v.y | v.z | v.w;
+                    if (CHECK_CR) cr_acc |= cr_any(v.x) | cr_any(v.y) | cr_any(v.z) | cr_any(v.w);
+                    const uint32_t NL = 0x0a0a0a0au, K = 0x7f7f7f7fu;
+                    const uint32_t x0 = (v.x ^ NL) + K, x1 = (v.y ^ NL) + K, x2 = (v.z ^ NL) + K, x3 = (v.w ^ NL) + K;
+                    const uint32_t m = ((~x0 & H) >> 7) | ((~x1 & H) >> 6) | ((~x2 & H) >> 5) | ((~x3 & H) >> 4);
+                    // no branch: the code is stored whether the chunk has a start or not -- a miss lands on the slot the
+                    // next hit overwrites, and the last slot is never counted
+                    const uint32_t code = (((uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j) << 5) | ((uint32_t)__ffs((int)m) - 1u);
+                    myhits[cnt < (uint32_t)(K1_LHCAP - 1) ? cnt : (uint32_t)(K1_LHCAP - 1)] = (uint16_t)code;
+                    cnt += m != 0u ? 1u : 0u;
+                    multi |= m & (m - 1u);                    // two starts within 16 bytes
+                }
             }
             if (multi) hi_acc |= 0x80u;                       // tiny lines: the byte-wise path sorts them out
         } else {
@@ -490,7 +502,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 k1_list_hits(myhits, K1_LHCAP, k1_chunk_mask(v, off, wlen), (uint32_t)lane * K1_LANE_CHUNKS + (uint32_t)j, cnt);
             }
         }
-        if (cnt > (uint32_t)K1_LHCAP) hi_acc |= 0x80u;        // a crowd of short lines: likewise
+        if (cnt > (uint32_t)(K1_LHCAP - 1)) hi_acc |= 0x80u;  // a crowd of short lines: likewise
         // look-ahead bytes: only the odd-byte tests
         for (uint32_t off = (uint32_t)K1_TILE + (uint32_t)lane * 16u; off < wlen; off += 512u) {
             const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
