@@ -104,6 +104,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// atomicAdd(p, 1) whose result may stay in flight: written as PTX so that the compiler does not turn it into its
+// warp-aggregated form, which shuffles the result out right away and so waits for it
+__device__ __forceinline__ uint32_t atom_inc_u32(unsigned int *p) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    return old;
+}
+
 // pull [src, src + bytes) into L2 ahead of the bulk copy that will want it (bytes a multiple of 16)
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     bool ticket_taken = false;                                // (warp-uniform)
     for (;;) {
         // tiles in increasing order (see k1_tile_resolve); usually taken during the last parse step of the tile before
-        if (!ticket_taken && lane == 0) ticket = (int)atomicAdd(&a.st->next_tile, 1u);
+        if (!ticket_taken && lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);
         const int tile = __shfl_sync(0xffffffffu, ticket, 0);
         ticket_taken = false;
         if (tile >= a.n_tiles) break;
@@ -551,10 +551,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 if (idx < (uint32_t)K1_WCAP) sm.starts[idx] = myhits[k];
             }
         }
-        if (buffered) {                                       // (res overlays the lane lists just copied)
-            __syncwarp();
-            for (uint32_t i = (uint32_t)lane; i < n_tile_lines; i += 32u) res[i] = 0xffffu;
-        }
+        if (buffered) __syncwarp();                           // (res overlays the lane lists just copied)
         // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
         for (uint32_t done = 0; done < n_tile_lines; done += K1_WCAP) {
             __syncwarp();
@@ -601,7 +598,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             __syncwarp();
             for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
                 if (l0 + 32u >= n_pass && done + n_pass == n_tile_lines) {   // last step of the tile: the next ticket,
-                    if (lane == 0) ticket = (int)atomicAdd(&a.st->next_tile, 1u);   // its latency hidden behind the parse
+                    if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);   // its latency hidden behind the parse
                     ticket_taken = true;
                 }
                 const bool have = l0 + (uint32_t)lane < n_pass;
@@ -628,6 +625,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         }
                     }
                 }
+                if (buffered && to_detail) res[line_idx] = 0xffffu;   // emitted from the queue, not by flush_pending
                 uint32_t len_hint = 0;                        // up to the '\n' in front of the next listed start
                 if (to_detail && l + 1u < n_pass) {
                     const uint32_t c1 = sm.starts[l + 1u];

@@ -169,13 +169,11 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     bad |= buf[i] != '\t';
     i++;
     if (bad) return ST_DETAIL;
-    int32_t site = -1;
-    if ((int64_t)pos <= cc.max_pos) {                  // site_find (sites.cuh) on the cached contig
-        const int64_t bit = cc.bit_base + (int64_t)pos;
-        const uint32_t bw = sites.bits[bit >> 5], bb = (uint32_t)bit & 31u;
-        if ((bw >> bb) & 1u) site = (int32_t)(sites.rank[bit >> 5] + (uint32_t)popc32(bw & ((1u << bb) - 1u)));
-    }
-    if (!all_positions && site < 0) return ST_SKIP;
+    // site_find (sites.cuh) on the cached contig: the bitmap word is asked for here; in all-positions mode it is only
+    // looked at when the line is done, so its latency hides behind the rest of the parse
+    const int64_t bit = cc.bit_base + (int64_t)pos;
+    const uint32_t bw = (int64_t)pos <= cc.max_pos ? sites.bits[bit >> 5] : 0u, bb = (uint32_t)bit & 31u;
+    if (!all_positions && !((bw >> bb) & 1u)) return ST_SKIP;
     const unsigned ref = buf[i];
     bad = ((ref | 0x20u) - 'a') >= 26u;                // a letter: '.'/',' stand for REF / ref (pileup.py:255-256)
     bad |= buf[i + 1] != '\t';
@@ -248,7 +246,7 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     // ---- call (pileup.py:550-588): the reference base wins outright ---------------------------------
     const uint32_t dc = a_dc >> 7, dot = a_dot >> 7;
     if (dc <= nb - dc) return ST_DETAIL;
-    out->site = site;
+    out->site = ((bw >> bb) & 1u) ? (int32_t)(sites.rank[bit >> 5] + (uint32_t)popc32(bw & ((1u << bb) - 1u))) : -1;
     out->end = q0 + nb;
     out->base = (uint8_t)ref;
     out->fail = filter_mask(nb, dc, dot, dc - dot, p);
