@@ -1,0 +1,9 @@
+#!/bin/bash
+# timing-only A/B, interleaved, three rounds: profiles/ab2.sh <variant names...> ("base" = in-tree)
+for round in 1 2 3; do
+for v in "$@"; do
+  if [ "$v" = base ]; then unset SNPGPU_LIB; else export SNPGPU_LIB=$PWD/variants/libsnpgpu_$v.so; fi
+  echo "$v all:   $(python profiles/run_k1.py all 10 2>&1 | tail -1 | cut -c1-75)"
+  echo "$v sites: $(python profiles/run_k1.py sites 10 2>&1 | tail -1 | cut -c1-75)"
+done
+done

@@ -21,11 +21,24 @@
 //     slot: the index of a tile's first line comes from a decoupled look-back over the tiles' line counts.
 // Algorithmic traffic: every text byte read once (+12 % look-ahead re-read, an L2 hit), 2 B written per line.
 #include "internal.h"
+#include <stdio.h>
 #include "line_fast.cuh"
 #include "line_quick.cuh"
 #include "line_general.cuh"
 
 namespace snpgpu {
+
+// Tuning builds (profiles/variant.sh prof -DK1_PROF): cycles lane 0 of every warp spends per phase, summed over all
+// warps into the unused tail of the status block and printed by the finish kernel.  Compiled out of the product.
+#ifdef K1_PROF
+#define PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[16] = {0}
+#define PROF(i) do { const long long prof_n = clock64(); prof_acc[i] += (unsigned long long)(prof_n - prof_t); prof_t = prof_n; } while (0)
+#define PROF_FLUSH(st) do { if (lane == 0) for (int i = 0; i < 16; i++) atomicAdd(reinterpret_cast<unsigned long long *>(st) + 8 + i, prof_acc[i]); } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_FLUSH(st)
+#endif
 
 struct K1Warp {                                 // one warp's slice of shared memory
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
@@ -381,6 +394,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     }
     __syncwarp();
     uint32_t parity = 0, n_dq = 0, n_gq = 0, n_parsed = 0;
+    PROF_DECL;
     unsigned long long n_lines = 0;
     K1Cold cs{0, 0u, 0u};
     constexpr bool CHECK_CR = !ALL || HAS_QUAL;
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         // tiles in increasing order (see k1_tile_resolve); usually taken during the last parse step of the tile before
         if (!ticket_taken && lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);
         const int tile = __shfl_sync(0xffffffffu, ticket, 0);
+        PROF(0);                                              // (waiting for the warp's slowest lane and the ticket)
         ticket_taken = false;
         if (tile >= a.n_tiles) break;
         if (drained) {   // a lane met another contig (line_fast.cuh moved its hint): the warp follows the last such lane
@@ -451,13 +466,17 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
+        PROF(1);
         flush_pending();                                      // the previous tile's results, while this window loads
+        PROF(2);
         if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines too: every tile they belong to is resolved now
             drained = true;
             const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
             n_dq = r & 0xffffu; n_gq = r >> 16;
         }
+        PROF(3);
         if (bulk) { mbar_wait(&sm.bar, parity); parity ^= 1u; }
+        PROF(4);
         __syncwarp();
         // ---- scan: every lane lists the line starts of its chunks as it finds them -------------------
         uint32_t hi_acc = 0, cr_acc = 0, cnt = 0;
@@ -503,6 +522,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             }
         }
         if (cnt > (uint32_t)(K1_LHCAP - 1)) hi_acc |= 0x80u;  // a crowd of short lines: likewise
+        PROF(5);
         // look-ahead bytes: only the odd-byte tests
         for (uint32_t off = (uint32_t)K1_TILE + (uint32_t)lane * 16u; off < wlen; off += 512u) {
             const uint4 v = *reinterpret_cast<const uint4 *>(sm.buf + off);
@@ -542,6 +562,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 slot0 = k1_tile_resolve(a, tile, n_tile_lines, lane);
             }
         }
+        PROF(6);
         // ---- the warp's list, file order (the first K1_WCAP starts; more -> later passes scan again) -----
         {
             const uint32_t skip = file_start ? 1u : 0u;
@@ -552,6 +573,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             }
         }
         if (buffered) __syncwarp();                           // (res overlays the lane lists just copied)
+        PROF(7);
         // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
         for (uint32_t done = 0; done < n_tile_lines; done += K1_WCAP) {
             __syncwarp();
@@ -596,6 +618,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u)
                 perm[hist[(keys >> (4u * k)) & 15u] + (uint32_t)((ranks >> (8u * k)) & 0xffu)] = (uint8_t)l;
             __syncwarp();
+            PROF(8);
             for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
                 if (l0 + 32u >= n_pass && done + n_pass == n_tile_lines) {   // last step of the tile: the next ticket,
                     if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);   // its latency hidden behind the parse
@@ -614,7 +637,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                     to_detail = true;
                     if (!HAS_QUAL) {
                         QuickLine q;
+                        PROF(9);
                         const int st = quick_line(sm.buf, s, wlen, a.sites, cc, a.p, ALL, &q);
+                        PROF(10);
                         if (st == ST_SKIP) to_detail = false;
                         else if (st == ST_OK && !(q.end == wlen && !eof)) {   // (a line that leaves the window goes on)
                             const uint16_t v = k1_cell(a, q.base, q.fail, q.site, base + s);
@@ -632,6 +657,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                     len_hint = (c1 >> 5) * 16u + (c1 & 7u) * 4u + ((c1 >> 3) & 3u) - s;
                 }
                 const unsigned long long entry = k1_entry(line_idx, len_hint, base + s);
+                PROF(11);
                 n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
                 if (n_dq >= 32u) {                            // leaves both queues below 32
                     drained = true;
@@ -641,13 +667,19 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 }
             }
         }
+        PROF(12);
         n_lines += n_tile_lines;
     }
     {
+        PROF(0);
         flush_pending();
+        PROF(13);
         const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
+        PROF(14);
         k1_drain_general(a, sm, cs, lane, r >> 16, true);
     }
+    PROF(15);
+    PROF_FLUSH(a.st);
     // ---- statistics -------------------------------------------------------------------------------
     uint32_t np = n_parsed + cs.n_parsed, ng = cs.n_general;
 #pragma unroll
@@ -671,6 +703,16 @@ __global__ void k1_finish_kernel(const unsigned long long *site_cells, const int
         unsigned long long c = site_cells[snp_unique[k]];
         row_out[k] = c ? (uint8_t)(c & 0xffu) : (uint8_t)'-';
     }
+#ifdef K1_PROF
+    if (k == 0) {
+        const unsigned long long *pc = reinterpret_cast<const unsigned long long *>(st) + 8;
+        unsigned long long tot = 0;
+        for (int i = 0; i < 16; i++) tot += pc[i];
+        printf("K1_PROF total %llu Mcycles:", tot / 1000000ull);
+        for (int i = 0; i < 16; i++) printf(" p%d %.1f%%", i, 100.0 * (double)pc[i] / (double)tot);
+        printf("\n");
+    }
+#endif
     if (k == 0 && out) {
         out->n_lines = st->n_lines;
         out->n_parsed = st->n_parsed;
