@@ -169,8 +169,8 @@ def device_step(w, dist, world):
         n_uniq = ctx.merge_sites_dev(allkeys.data_ptr(), owner.data_ptr(), allkeys.numel(), gu.data_ptr(),
                                      gc.data_ptr(), gs.data_ptr())
         local = gu[:n_uniq]
-    positions = local.cpu().numpy()
-    sites = build_sites(ctx, positions)
+    # the merged list never leaves HBM: K2's sorted unique keys -> the table K1 probes (snpgpu_sites_create_from_keys_dev)
+    sites = w.lib.Sites.from_keys_dev(ctx, [CONTIG], [w.args.genome_len], local.data_ptr(), n_uniq)
     matrix = torch.empty((w.n, max(n_uniq, 1)), dtype=torch.uint8, device="cuda")
     for i in range(w.n):
         ctx.pileup_consensus_dev(w.texts[i].data_ptr(), w.nbytes[i], sites, w.params, w.lib.MODE_ALL,
@@ -322,11 +322,16 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    from snp_pipeline_b200 import _lib, device
+    numa_cpus = device.bind_to_gpu_cpus(local_rank)           # pinned host buffers next to the GPU (e2e leg)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from snp_pipeline_b200 import _lib
     ctx = _lib.Context(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one explicit stream for torch's ops, the library's kernels and the timing events (the legacy default stream has
+    # handle 0, which snpgpu_set_stream reads as "the context's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     w = Workload(ctx, torch, args, rank)
 
     def barrier():
@@ -394,7 +399,6 @@ def main():
     # ---- end to end through the host-buffer C ABI ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        ctx.set_stream(None)
         pool, pool_n, owners = [], [], []
         for k in range(min(args.host_pool, w.n)):
             arr, owner = ctx.pinned_array(w.nbytes[k])
@@ -437,6 +441,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
             "n_sites": int(n_sites), "matrix_cells_per_s": world * w.n * n_sites / (ms_step * 1e-3),
             "text_gb_per_gpu": w.total_text / 1e9,
         }

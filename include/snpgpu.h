@@ -94,6 +94,15 @@ int  snpgpu_sites_create(snpgpu_ctx *ctx,
                          const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp,
                          const int32_t *exc_contig, const int64_t *exc_pos, size_t n_exc,
                          snpgpu_sites **out);
+/* The same table built on the device from K2's output, when merge_sites and call_consensus run in one process: the
+ * list that the reference writes to snplist.txt (utils.py:1056-1070) and reads back (utils.py:1073-1088,
+ * call_consensus.py:133) stays in HBM.  keys_dev: n_keys sorted unique (chrom_rank << 32 | pos) keys in device memory,
+ * as snpgpu_merge_sites_dev leaves them; every key is a snplist entry, in that order; contig_len[c] bounds the
+ * positions of contig c (chrom_rank c).  Nothing is copied back, nothing is synchronised; the table is valid for work
+ * enqueued afterwards on the context's stream, and snpgpu_sites_destroy hands its memory back in stream order. */
+int  snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names, const int32_t *name_off,
+                                       int32_t n_contigs, const int64_t *contig_len, const uint64_t *keys_dev,
+                                       size_t n_keys, snpgpu_sites **out);
 void snpgpu_sites_destroy(snpgpu_sites *sites);
 size_t snpgpu_sites_n_snp(const snpgpu_sites *sites);
 

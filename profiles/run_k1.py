@@ -13,7 +13,9 @@ mode = _lib.MODE_SITES if len(sys.argv) > 1 and sys.argv[1] == "sites" else _lib
 n_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 G = int(os.environ.get("GENOME_LEN", "5000000"))
 ctx = _lib.Context(0)
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
 spec = _lib.SynthSpec(20261017, 0, G, 24, G // 100, 0.05, 0.0)
 cap = G * 112 + 4096
 buf = torch.empty(cap, dtype=torch.uint8, device="cuda")

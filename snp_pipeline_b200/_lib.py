@@ -21,7 +21,7 @@ FAIL_RAWDPTH, FAIL_VARFREQ, FAIL_DEPTH, FAIL_STRDPTH, FAIL_STRBIAS, FAIL_REGION 
 EXPORTS = [
     "snpgpu_abi_version", "snpgpu_create", "snpgpu_destroy", "snpgpu_last_error", "snpgpu_set_stream",
     "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_enable_timing",
-    "snpgpu_kernel_time", "snpgpu_sites_create",
+    "snpgpu_kernel_time", "snpgpu_sites_create", "snpgpu_sites_create_from_keys_dev",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
     "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
@@ -111,6 +111,8 @@ def load():
     L.snpgpu_kernel_time.argtypes = [vp, ctypes.c_int, P(ctypes.c_double), P(u64)]
     L.snpgpu_sites_create.restype = ctypes.c_int
     L.snpgpu_sites_create.argtypes = [vp, ctypes.c_char_p, vp, i32, vp, vp, sz, vp, vp, sz, P(vp)]
+    L.snpgpu_sites_create_from_keys_dev.restype = ctypes.c_int
+    L.snpgpu_sites_create_from_keys_dev.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int32, vp, vp, sz, P(vp)]
     L.snpgpu_sites_destroy.restype = None
     L.snpgpu_sites_destroy.argtypes = [vp]
     L.snpgpu_sites_n_snp.restype = sz
@@ -167,6 +169,26 @@ class Sites(object):
                                          len(snp_list), _np_ptr(ec), _np_ptr(ep), len(excluded), ctypes.byref(h))
         ctx._check(rc)
         self.handle = h
+
+    @classmethod
+    def from_keys_dev(cls, ctx, contigs, contig_len, keys_ptr, n_keys):
+        """Device fast path: the table straight from merge_sites_dev's sorted unique keys (device pointer), no host
+        round trip.  contigs: names in chromosome-string order (index = chrom_rank); contig_len: their lengths."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.contigs = list(contigs)
+        enc = [n.encode("utf-8") for n in self.contigs]
+        blob = b"".join(enc)
+        off = np.zeros(len(enc) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(n) for n in enc])
+        lens = np.ascontiguousarray(contig_len, dtype=np.int64)
+        self.n_snp = int(n_keys)
+        h = ctypes.c_void_p()
+        rc = ctx.lib.snpgpu_sites_create_from_keys_dev(ctx.handle, blob, _np_ptr(off), len(enc), _np_ptr(lens),
+                                                       ctypes.c_void_p(int(keys_ptr)), int(n_keys), ctypes.byref(h))
+        ctx._check(rc)
+        self.handle = h
+        return self
 
     @classmethod
     def from_arrays(cls, ctx, contigs, snp_contig, snp_pos, exc_contig=None, exc_pos=None):

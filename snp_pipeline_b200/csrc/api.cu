@@ -47,6 +47,8 @@ struct snpgpu_ctx {
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
     DevBuf synth_tmp, synth_n;
+    DevBuf k3_tmp;
+    std::vector<std::pair<void *, size_t>> sites_pool;   // blobs of destroyed device-built site tables, reused in stream order
     size_t arena_want = 1 << 20;
     bool   timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];     // pending event pairs per kernel id
@@ -76,6 +78,8 @@ struct snpgpu_sites {
     size_t n_snp = 0, n_unique = 0;
     int n_contigs = 0;
     void *blob = nullptr;                     // one device allocation holding every array below
+    size_t blob_bytes = 0;
+    bool pooled = false;                      // built by snpgpu_sites_create_from_keys_dev: the blob goes back to the context
     SiteTable table;                          // device pointers
     int32_t *snp_unique = nullptr;            // device, n_snp: unique-site index of snplist entry k
 };
@@ -128,8 +132,10 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
                      &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
-                     &ctx->synth_tmp, &ctx->synth_n};
+                     &ctx->synth_tmp, &ctx->synth_n, &ctx->k3_tmp};
     for (DevBuf *b : all) b->release();
+    for (auto &pr : ctx->sites_pool) cudaFree(pr.first);
+    ctx->sites_pool.clear();
     for (int k = 0; k < 2; k++)
         for (auto &pr : ctx->timed[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : ctx->spare_events) cudaEventDestroy(e);
@@ -141,7 +147,9 @@ const char *snpgpu_last_error(const snpgpu_ctx *ctx) { return ctx ? ctx->err.c_s
 
 int snpgpu_set_stream(snpgpu_ctx *ctx, void *stream) {
     if (!ctx) return SNPGPU_E_ARG;
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    cudaStream_t next = stream ? (cudaStream_t)stream : ctx->own_stream;
+    if (next != ctx->stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }   // pooled blobs are reused in stream order
+    ctx->stream = next;
     return SNPGPU_OK;
 }
 
@@ -253,9 +261,99 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
 
 void snpgpu_sites_destroy(snpgpu_sites *sites) {
     if (!sites) return;
+    if (sites->pooled && sites->ctx && sites->blob && sites->ctx->sites_pool.size() < 4) {
+        // whatever still reads the table was enqueued on the context's stream, and so is whatever reuses the blob
+        sites->ctx->sites_pool.emplace_back(sites->blob, sites->blob_bytes);
+        delete sites;
+        return;
+    }
     if (sites->ctx) { cudaSetDevice(sites->ctx->device); cudaStreamSynchronize(sites->ctx->stream); }
     if (sites->blob) cudaFree(sites->blob);
     delete sites;
+}
+
+// The site table straight from K2's output (k3_sites.cu): keys_dev = n_keys sorted unique (chrom_rank << 32 | pos)
+// keys in device memory, as snpgpu_merge_sites_dev writes them; contig_len[c] bounds the positions of contig c.
+// Every key is a snplist entry, in this order (the order of snplist.txt, utils.py:1068); no exclude list.
+// Nothing is copied back and nothing is synchronised: the table is ready in stream order.
+int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names, const int32_t *name_off,
+                                      int32_t n_contigs, const int64_t *contig_len, const uint64_t *keys_dev,
+                                      size_t n_keys, snpgpu_sites **out) {
+    if (!ctx || !out || n_contigs <= 0 || !contig_names || !name_off || !contig_len || (n_keys && !keys_dev))
+        return fail(ctx, SNPGPU_E_ARG, "sites_create_from_keys_dev: bad argument");
+    if (n_keys >= ((size_t)1 << 31)) return fail(ctx, SNPGPU_E_ARG, "sites_create_from_keys_dev: too many keys");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    HostSites h;
+    const char *why = "";
+    int hrc = build_host_sites(contig_names, name_off, n_contigs, nullptr, nullptr, 0, nullptr, nullptr, 0, &h, &why);
+    if (hrc) {
+        static thread_local std::string msg;
+        msg = std::string("sites_create_from_keys_dev: ") + why;
+        return fail(ctx, hrc == 1 ? SNPGPU_E_ARG : hrc, msg.c_str());
+    }
+    int64_t total_bits = 0;
+    for (int c = 0; c < n_contigs; c++) {
+        if (contig_len[c] < 0 || contig_len[c] >= ((int64_t)1 << 31))
+            return fail(ctx, SNPGPU_E_DOMAIN, "sites_create_from_keys_dev: contig length outside [0, 2^31)");
+        h.max_pos[c] = contig_len[c];
+        h.bit_base[c] = total_bits;
+        total_bits += (contig_len[c] + 1 + 31) / 32 * 32;
+    }
+    if (total_bits > ((int64_t)1 << 33)) return fail(ctx, 18, "sites_create_from_keys_dev: site bitmap above 1 GiB");
+    const size_t n_words = (size_t)(total_bits / 32) + 1;
+    // small host-built sections, packed into one staging buffer -> one copy
+    std::vector<uint8_t> stage;
+    auto put = [&](const void *src, size_t bytes) { size_t off = stage.size(); stage.resize(off + ((bytes + 255) & ~(size_t)255));
+                                                     if (bytes) memcpy(stage.data() + off, src, bytes); return off; };
+    const size_t o_names4 = put(h.names4.data(), h.names4.size() * 4), o_off4 = put(h.off4.data(), h.off4.size() * 4);
+    const size_t o_len1 = put(h.len1.data(), h.len1.size() * 4), o_names = put(h.names.data(), h.names.size());
+    const size_t o_noff = put(h.name_off.data(), h.name_off.size() * 4), o_base = put(h.bit_base.data(), h.bit_base.size() * 8);
+    const size_t o_max = put(h.max_pos.data(), h.max_pos.size() * 8);
+    const size_t small = stage.size();
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_bits = small, o_rank = o_bits + up(n_words * 4), o_flags = o_rank + up(n_words * 4);
+    const size_t o_su = o_flags + up(n_keys + 1), total = o_su + up((n_keys + 1) * 4);
+    snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
+    if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create_from_keys_dev: host allocation");
+    for (size_t k = 0; k < ctx->sites_pool.size(); k++) {
+        if (ctx->sites_pool[k].second >= total) {
+            s->blob = ctx->sites_pool[k].first; s->blob_bytes = ctx->sites_pool[k].second;
+            ctx->sites_pool.erase(ctx->sites_pool.begin() + (long)k);
+            break;
+        }
+    }
+    if (!s->blob) {
+        const size_t want = total + total / 4;                  // room for the next, slightly larger, list
+        cudaError_t e = cudaMalloc(&s->blob, want);
+        if (e != cudaSuccess) { delete s; return fail(ctx, SNPGPU_E_NOMEM, "sites_create_from_keys_dev: cudaMalloc", e); }
+        s->blob_bytes = want;
+    }
+    s->pooled = true;
+    auto at = [&](size_t off) { return (uint8_t *)s->blob + off; };
+    cudaError_t e = cudaMemcpyAsync(s->blob, stage.data(), small, cudaMemcpyHostToDevice, ctx->stream);   // pageable: staged before return
+    if (e == cudaSuccess && ctx->k3_tmp.ensure(k3_scan_bytes(n_words) + 256) != cudaSuccess) e = cudaErrorMemoryAllocation;
+    int launched = -1;
+    if (e == cudaSuccess)
+        launched = k3_launch(ctx->stream, (const unsigned long long *)keys_dev, n_keys, n_contigs, (const int64_t *)at(o_base),
+                             (const int64_t *)at(o_max), (uint32_t *)at(o_bits), (uint32_t *)at(o_rank), n_words,
+                             at(o_flags), (int32_t *)at(o_su), ctx->k3_tmp.p, ctx->k3_tmp.cap);
+    if (e != cudaSuccess || launched < 0) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s->blob); delete s;
+        return fail(ctx, SNPGPU_E_CUDA, "sites_create_from_keys_dev: launch", e != cudaSuccess ? e : cudaGetLastError());
+    }
+    ctx->launches += (uint64_t)launched;
+    s->ctx = ctx; s->n_snp = n_keys; s->n_unique = n_keys; s->n_contigs = n_contigs;
+    s->table.n_contigs = n_contigs; s->table.n_unique = (int32_t)n_keys;
+    s->table.names4 = (const uint32_t *)at(o_names4); s->table.off4 = (const int32_t *)at(o_off4);
+    s->table.len1 = (const int32_t *)at(o_len1); s->table.names = (const uint8_t *)at(o_names);
+    s->table.name_off = (const int32_t *)at(o_noff); s->table.bit_base = (const int64_t *)at(o_base);
+    s->table.max_pos = (const int64_t *)at(o_max); s->table.bits = (const uint32_t *)at(o_bits);
+    s->table.rank = (const uint32_t *)at(o_rank); s->table.flags = at(o_flags);
+    s->snp_unique = (int32_t *)at(o_su);
+    *out = s;
+    return SNPGPU_OK;
 }
 
 size_t snpgpu_sites_n_snp(const snpgpu_sites *sites) { return sites ? sites->n_snp : 0; }

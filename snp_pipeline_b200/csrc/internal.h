@@ -21,6 +21,12 @@ int    k5_launch_tally(cudaStream_t stream, const uint8_t *text, size_t nbytes, 
                        const unsigned long long *offsets, size_t n_rec, snpgpu_vcf_record *rec_out, snpgpu_vcf_alt *alt_out,
                        size_t alt_cap, unsigned long long *alt_count, PileupStatusDev *st, uint8_t *arena, size_t arena_cap);
 
+// k3_sites.cu
+size_t k3_scan_bytes(size_t n_words);
+int    k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
+                 const int64_t *max_pos, uint32_t *bits, uint32_t *rank, size_t n_words, uint8_t *flags,
+                 int32_t *snp_unique, void *tmp, size_t tmp_bytes);
+
 // k2_merge.cu
 // sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller
 size_t k2_workspace_bytes(size_t n);

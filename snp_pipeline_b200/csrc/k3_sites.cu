@@ -1,0 +1,63 @@
+// k3_sites.cu -- the site table built on the device from K2's output (no trip through the host).
+//
+// Between merge_sites and call_consensus the reference passes the site list through snplist.txt
+// (utils.write_list_of_snps utils.py:1056-1070 -> utils.read_snp_position_list utils.py:1073-1088) and every
+// call_consensus process builds its set of positions from that file (call_consensus.py:133, :147-151).  When both
+// steps run in one process on one GPU the list never has to leave HBM: the sorted unique keys K2 wrote are turned
+// into the table K1 probes (sites.cuh) by two small kernels and one device scan (CUB: library code, as in k2_merge.cu).
+#include "internal.h"
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+namespace snpgpu {
+
+// one bit per site; flags / snp_unique: every key is a snplist entry and the list is already in snplist order
+__global__ void k3_set_bits_kernel(const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
+                                   const int64_t *max_pos, uint32_t *bits, uint8_t *flags, int32_t *snp_unique) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    const int c = (int)(k >> 32);
+    const int64_t p = (int64_t)(k & 0xffffffffull);
+    flags[i] = SITE_SNP;
+    snp_unique[i] = (int32_t)i;
+    if (c < n_contigs && p <= max_pos[c]) {                  // (a key outside the caller's contig lengths: no line can hit it)
+        const int64_t b = bit_base[c] + p;
+        atomicOr(&bits[b >> 5], 1u << (b & 31));
+    }
+}
+
+struct PopcOp {
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &w) const {
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)__popc(w);
+#else
+        return (uint32_t)__builtin_popcount(w);
+#endif
+    }
+};
+
+size_t k3_scan_bytes(size_t n_words) {
+    size_t b = 0;
+    cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(nullptr, PopcOp());
+    cub::DeviceScan::ExclusiveSum(nullptr, b, in, (uint32_t *)nullptr, (int64_t)n_words);
+    return b;
+}
+
+// bits / rank: n_words words each, bits zeroed here; returns the number of kernels launched, or < 0
+int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
+              const int64_t *max_pos, uint32_t *bits, uint32_t *rank, size_t n_words, uint8_t *flags,
+              int32_t *snp_unique, void *tmp, size_t tmp_bytes) {
+    if (cudaMemsetAsync(bits, 0, n_words * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    int launches = 0;
+    if (n) {
+        k3_set_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, flags,
+                                                                          snp_unique);
+        launches++;
+    }
+    cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(bits, PopcOp());
+    if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, rank, (int64_t)n_words, stream) != cudaSuccess) return -1;
+    return launches + 2;
+}
+
+}  // namespace snpgpu

@@ -300,6 +300,37 @@ def test_synthetic_sample_device_resident(ctx, genome_len, sample):
 
 
 # ------------------------------------------------------------------------------------------ K2
+def test_site_table_built_on_device(ctx):
+    """snpgpu_sites_create_from_keys_dev (K2's keys -> site table, no host round trip) against the host-built table:
+    same consensus rows, same per-line calls, on two contigs."""
+    import torch
+    from snp_pipeline_b200 import _lib
+    rng = random.Random(77)
+    contigs = ["chrA|1|", "chrB.22"]                       # chromosome-string order = rank order
+    lens = [3000, 1200]
+    text = (linegen.pileup_text(5, 3000, chrom=contigs[0]) + linegen.pileup_text(6, 1200, chrom=contigs[1])).encode()
+    snps = sorted([(0, p) for p in rng.sample(range(1, 3001), 300)] + [(1, p) for p in rng.sample(range(1, 1201), 150)])
+    keys = np.array([(c << 32) | p for c, p in snps], dtype=np.uint64)
+    keys_dev = torch.from_numpy(keys.view(np.int64)).cuda()
+    host = _lib.Sites.from_arrays(ctx, contigs, np.array([c for c, _ in snps], np.int32), np.array([p for _, p in snps], np.int64))
+    p = _lib.make_params(min_cons_depth=3)
+    for mode in (_lib.MODE_SITES, _lib.MODE_ALL):
+        want = ctx.pileup_consensus(text, host, p, mode, want_lines=mode == _lib.MODE_ALL)
+        for _ in range(3):                                 # (the second and third tables reuse the first one's memory)
+            dev = _lib.Sites.from_keys_dev(ctx, contigs, lens, keys_dev.data_ptr(), keys.size)
+            got = ctx.pileup_consensus(text, dev, p, mode, want_lines=mode == _lib.MODE_ALL)
+            dev.close()
+            assert got[0] == want[0]
+            assert got[1].n_parsed == want[1].n_parsed
+            if mode == _lib.MODE_ALL:
+                assert np.array_equal(got[2], want[2])
+    host.close()
+    empty = _lib.Sites.from_keys_dev(ctx, contigs, lens, 0, 0)
+    row, stats = ctx.pileup_consensus(text, empty, p, _lib.MODE_SITES)[:2]
+    assert row == b"" and stats.n_parsed == 0
+    empty.close()
+
+
 @pytest.mark.parametrize("dataset,vcf", [("lambda", "var.flt.vcf"), ("agona", "var.flt.vcf"),
                                          ("listeria", "var.flt.vcf")])
 def test_merge_sites_golden(ctx, golden_dir, dataset, vcf):
