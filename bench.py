@@ -184,15 +184,25 @@ def device_step(w, dist, world):
     return n_uniq, matrix, d
 
 
-def host_step(w, pool, pool_n, bufs):
-    """One end-to-end pass through the host-buffer C-ABI calls (what a ctypes user of the library makes)."""
-    ctx, lib = w.ctx, w.lib
+def host_step(w, pool, pool_n, bufs, dist=None, world=1):
+    """One end-to-end pass through the host-buffer C-ABI calls (what a ctypes user of the library makes).  With more
+    than one rank the two exchange steps of device_step() happen here too, from and to host memory."""
+    from snp_pipeline_b200 import sharding
+    torch, ctx, lib = w.torch, w.ctx, w.lib
     uniq, cnt, samples = ctx.merge_sites(w.keys_host, w.samp_host)
+    h2d = w.keys_host.nbytes + w.samp_host.nbytes
+    d2h = uniq.nbytes + cnt.nbytes + samples.nbytes
+    if world > 1:                                              # the global union: all-gather of the per-rank lists
+        local = torch.from_numpy(uniq.view(np.int64)).cuda()
+        parts = sharding.allgather_varlen(local, dist, world)
+        allkeys = torch.cat(parts).cpu().numpy().view(np.uint64)
+        owner = np.concatenate([np.full(int(p.numel()), r, dtype=np.uint32) for r, p in enumerate(parts)])
+        h2d += uniq.nbytes + allkeys.nbytes + owner.nbytes
+        uniq, cnt, samples = ctx.merge_sites(allkeys, owner)
+        d2h += allkeys.nbytes + uniq.nbytes + cnt.nbytes + samples.nbytes
     sites = build_sites(ctx, uniq)
     n_sites = uniq.size
     rows, lines, stats = bufs
-    h2d = w.keys_host.nbytes + w.samp_host.nbytes
-    d2h = uniq.nbytes + cnt.nbytes + samples.nbytes
     for i in range(w.n):
         k = i % len(pool)
         rc = ctx.lib.snpgpu_pileup_consensus(ctx.handle, ctypes.c_void_p(pool[k].ctypes.data), pool_n[k], sites.handle,
@@ -202,11 +212,21 @@ def host_step(w, pool, pool_n, bufs):
         h2d += pool_n[k]
         d2h += n_sites + 2 * stats.n_lines + ctypes.sizeof(stats)
     m = rows[:, :n_sites]
-    d = np.zeros((w.n, w.n), dtype=np.int32)
-    ctx._check(ctx.lib.snpgpu_pairwise_distance(ctx.handle, ctypes.c_void_p(rows.ctypes.data), w.n, n_sites,
-                                                rows.shape[1], ctypes.c_void_p(d.ctypes.data)))
-    h2d += w.n * rows.shape[1]
-    d2h += d.nbytes
+    if world == 1:
+        d = np.zeros((w.n, w.n), dtype=np.int32)
+        ctx._check(ctx.lib.snpgpu_pairwise_distance(ctx.handle, ctypes.c_void_p(rows.ctypes.data), w.n, n_sites,
+                                                    rows.shape[1], ctypes.c_void_p(d.ctypes.data)))
+        h2d += w.n * rows.shape[1]
+        d2h += d.nbytes
+    else:                                                      # every rank needs every row: all-gather, then its stripe
+        block = torch.from_numpy(rows).cuda()
+        full = sharding.allgather_rows(block, dist, world)
+        dd = torch.empty((w.n, full.shape[0]), dtype=torch.int32, device="cuda")
+        lo = w.rank * w.n
+        ctx.pairwise_distance_dev(full.data_ptr(), full.shape[0], n_sites, full.shape[1], lo, lo + w.n, dd.data_ptr())
+        d = dd.cpu().numpy()
+        h2d += rows.nbytes
+        d2h += d.nbytes
     sites.close()
     return m, d, h2d, d2h
 
@@ -409,12 +429,12 @@ def main():
         lines_arr, lines_owner = ctx.pinned_array(2 * (args.genome_len + 64))
         bufs = (rows, lines_arr.view(np.uint16), _lib.PileupStats())
         for _ in range(max(1, min(args.warmup, 1))):
-            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs)
+            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs, dist, world)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
-            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs)
+            m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs, dist, world)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
