@@ -345,6 +345,8 @@ def main():
     from snp_pipeline_b200 import _lib, device
     numa_cpus = device.bind_to_gpu_cpus(local_rank)           # pinned host buffers next to the GPU (e2e leg)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # its banner goes to stdout, in front of the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     # one explicit stream for torch's ops, the library's kernels and the timing events (the legacy default stream has
