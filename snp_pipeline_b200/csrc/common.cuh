@@ -26,16 +26,21 @@ struct PileupStatusDev {
 #ifndef K1_CFG_CHUNKS          // (tuning builds override these four on the nvcc command line)
 #define K1_CFG_CHUNKS 21
 #define K1_CFG_CTAS 4
-#define K1_CFG_LHCAP 12
+#define K1_CFG_LHCAP 11
 #define K1_CFG_QCAP 64
+#endif
+#ifndef K1_CFG_HELPER
+#define K1_CFG_HELPER 0
 #endif
 constexpr int K1_LANE_CHUNKS = K1_CFG_CHUNKS;             // 16-byte chunks one lane scans for newlines ...
 constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
 constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
 constexpr int K1_LOOK     = 1024;              // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_WARPS    = 4;                 // independent warps per CTA
-constexpr int K1_THREADS  = 32 * K1_WARPS;
+constexpr int K1_WARPS    = 4;                 // independent pipelines per CTA: a leader warp each ...
+constexpr int K1_HELPER   = K1_CFG_HELPER;     // ... plus (1) a helper warp that parses every other group of 32 lines.
+                                               // Off: at the 64 registers 32 warps per SM leave, the leader spills to L2 (measured -45 %)
+constexpr int K1_THREADS  = 32 * K1_WARPS * (1 + K1_HELPER);
 constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
 constexpr int K1_WCAP     = 256;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)

@@ -49,9 +49,30 @@ struct K1Warp {                                 // one warp's slice of shared me
     unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh (k1_entry)
     unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
     alignas(8) uint64_t bar;
+    // what the leader hands its helper warp for one pass (K1_HELPER), and what the helper hands back
+    unsigned long long h_base, h_slot0;         // file offset of the window; file-order index of the tile's first line
+    uint32_t h_wlen, h_n_pass, h_done;
+    uint32_t h_flags;                           // H_BUFFERED | H_EOF | H_EXIT
+    int32_t  h_cid;                             // the contig the leader expects
+    uint32_t h_declined;                        // helper -> leader: H_DECLINED (lines marked in starts[]) | H_DECLINED_FIRST
 };
+enum : uint32_t { H_BUFFERED = 1, H_EOF = 2, H_EXIT = 4, H_DECLINED = 1, H_DECLINED_FIRST = 2 };
+enum : uint32_t { START_MARK = 0x8000u, START_CODE = 0x7fffu };   // starts[]: bit 15 = "declined by the helper, the leader's to queue"
+static_assert((32 * K1_LANE_CHUNKS) << 5 <= (int)START_MARK, "start codes leave bit 15 free");
+
+// the two warps of a pipeline meet here (named barrier 1 + pipeline, 64 threads)
+__device__ __forceinline__ void pair_sync(int pipe) {          // (immediate barrier numbers: only 1 + K1_WARPS get reserved)
+    static_assert(K1_WARPS == 4, "one case per pipeline");
+    switch (pipe) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
 
 static_assert(K1_PAD >= (int)QUICK_PAD && K1_NAMEW % 4 == 0, "line_quick.cuh preconditions");
+static_assert(sizeof(K1Warp) * K1_WARPS * K1_CTAS_PER_SM + 1024 * K1_CTAS_PER_SM <= 228 * 1024, "shared memory per SM");
 size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
 
 // exact per-byte mask (0x80 where the byte equals '\n'), any byte values
@@ -380,14 +401,100 @@ __device__ __noinline__ void k1_relist(K1Warp &sm, int lane, uint32_t wlen, uint
     }
 }
 
+// One first-tier step of a pass: the lane's line l of the pass (have: it has one).  Returns true when the line has
+// to go on to the second tier; s = offset of the line in the window.  Shared by the leader and its helper warp.
+struct K1Pass {
+    unsigned long long base, slot0;
+    uint32_t wlen, done;
+    bool buffered, eof;
+};
+template <bool ALL>
+__device__ __forceinline__ bool k1_quick_step(const PileupArgs &a, K1Warp &sm, const ContigCache &cc, const K1Pass &ps,
+                                              bool have, uint32_t l, uint32_t code, uint32_t &s, uint32_t &n_parsed) {
+    uint16_t *res = sm.lanehits + K1_RES_OFF;
+    const uint32_t line_idx = ps.done + l;
+    s = 0;                                                    // code: chunk << 5 | flag bit 8*b + w  ->  byte 4*w + b of the chunk
+    if (have && code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
+    bool to_detail = false;
+    if (have) {
+        to_detail = true;
+        QuickLine q;
+        const int st = quick_line(sm.buf, s, ps.wlen, a.sites, cc, a.p, ALL, &q);
+        if (st == ST_SKIP) to_detail = false;
+        else if (st == ST_OK && !(q.end == ps.wlen && !ps.eof)) {     // (a line that leaves the window goes on)
+            const uint16_t v = k1_cell(a, q.base, q.fail, q.site, ps.base + s);
+            if (ps.buffered) res[line_idx] = v;
+            else if (ps.slot0 + line_idx < a.line_out_cap) a.line_out[ps.slot0 + line_idx] = v;
+            n_parsed++;
+            to_detail = false;
+        }
+    }
+    return to_detail;
+}
+
+// The helper warp of a pipeline (K1_HELPER): between two meetings with its leader it runs the first tier over every
+// other group of 32 lines of the pass the leader has listed and sorted.  It owns no queue: a line the first tier
+// declines is marked in starts[] (bit 15) and queued by the leader afterwards.
+template <bool ALL>
+__device__ __noinline__ void k1_helper(const PileupArgs &a, K1Warp &sm, int lane, int pipe) {
+    ContigCache cc;
+    contig_cache_attach(a.sites, -1, sm.cname, sm.cmask, K1_NAMEW, &cc);
+    const uint8_t *perm = reinterpret_cast<const uint8_t *>(sm.lanehits);
+    uint32_t n_parsed = 0;
+    for (;;) {
+        pair_sync(pipe);                                      // the leader has a pass ready (or is out of tiles)
+        const uint32_t flags = sm.h_flags;
+        if (flags & H_EXIT) break;
+        const int cid = sm.h_cid;
+        if (cid != cc.cid) contig_cache_attach(a.sites, cid, sm.cname, sm.cmask, K1_NAMEW, &cc);
+        K1Pass ps;
+        ps.base = sm.h_base; ps.slot0 = sm.h_slot0; ps.wlen = sm.h_wlen; ps.done = sm.h_done;
+        ps.buffered = (flags & H_BUFFERED) != 0u; ps.eof = (flags & H_EOF) != 0u;
+        const uint32_t n_pass = sm.h_n_pass;
+        uint32_t declined = 0;
+        for (uint32_t l0 = 32u; l0 < n_pass; l0 += 64u) {
+            const bool have = l0 + (uint32_t)lane < n_pass;
+            const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
+            const uint32_t code = have ? sm.starts[l] : 0u;
+            uint32_t s;
+            const bool to_detail = k1_quick_step<ALL>(a, sm, cc, ps, have, l, code, s, n_parsed);
+            if (to_detail) {
+                if (code == 0xffffu) declined |= H_DECLINED_FIRST;        // (the file's first line has no code to mark)
+                else { sm.starts[l] = (uint16_t)(code | START_MARK); declined |= H_DECLINED; }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) declined |= __shfl_xor_sync(0xffffffffu, declined, d);
+        if (lane == 0) sm.h_declined = declined;
+        pair_sync(pipe);                                      // done with the window and the lists
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_parsed += __shfl_xor_sync(0xffffffffu, n_parsed, d);
+    if (lane == 0 && n_parsed) atomicAdd(&a.st->n_parsed, (unsigned long long)n_parsed);
+}
+
 // HAS_QUAL: a minimum base quality is set (call_consensus -q > 0): every line goes straight to line_fast.cuh,
 // which pairs each base with its quality.  ALL: all-positions mode (compile-time so that the scan can drop its
 // '\r' test: there the parsers look at every byte of every line themselves).
 template <bool HAS_QUAL, bool ALL>
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(const __grid_constant__ PileupArgs a) {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // warps 0 .. K1_WARPS-1 lead the pipelines, warps K1_WARPS .. 2 K1_WARPS-1 help them (one warpgroup each, so that
+    // the register file can be re-split between the two roles)
+    const int warp = (int)(threadIdx.x >> 5) % K1_WARPS;      // the pipeline this warp belongs to
+    const bool helper = K1_HELPER && (int)(threadIdx.x >> 5) >= K1_WARPS;
     K1Warp &sm = reinterpret_cast<K1Warp *>(k1_smem_raw)[warp];
+    if (helper) {
+#if K1_HELPER && defined(K1_CFG_HELPER_REGS)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K1_CFG_HELPER_REGS));
+#endif
+        if (!HAS_QUAL) k1_helper<ALL>(a, sm, lane, warp);     // (with a minimum base quality the first tier is not used)
+        return;
+    }
+#if K1_HELPER && defined(K1_CFG_HELPER_REGS)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(128 - K1_CFG_HELPER_REGS));
+#endif
     if (lane == 0) {
         mbar_init(&sm.bar, 1);
         mbar_fence_init();
@@ -618,46 +725,30 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u)
                 perm[hist[(keys >> (4u * k)) & 15u] + (uint32_t)((ranks >> (8u * k)) & 0xffu)] = (uint8_t)l;
             __syncwarp();
+            // ---- the pass's lines, 32 per step; with a helper warp the leader takes the even steps ----------
+            const bool use_helper = K1_HELPER && !HAS_QUAL && n_pass > 32u;
+            K1Pass ps;
+            ps.base = base; ps.slot0 = slot0; ps.wlen = wlen; ps.done = done; ps.buffered = buffered; ps.eof = eof;
+            if (use_helper) {
+                if (lane == 0) {
+                    sm.h_base = base; sm.h_slot0 = slot0; sm.h_wlen = wlen; sm.h_n_pass = n_pass; sm.h_done = done;
+                    sm.h_flags = (buffered ? H_BUFFERED : 0u) | (eof ? H_EOF : 0u);
+                    sm.h_cid = cc.cid;
+                }
+                pair_sync(warp);                              // lists, permutation and hand-over block are complete
+            }
             PROF(8);
-            for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
-                if (l0 + 32u >= n_pass && done + n_pass == n_tile_lines) {   // last step of the tile: the next ticket,
-                    if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);   // its latency hidden behind the parse
-                    ticket_taken = true;
-                }
-                const bool have = l0 + (uint32_t)lane < n_pass;
-                const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
+            // a line for the second tier: its result slot is marked, it is queued with its length (up to the '\n' in
+            // front of the next listed start), and the queue is run when 32 wait
+            auto queue_line = [&](bool to_detail, uint32_t l, uint32_t s) {
                 const uint32_t line_idx = done + l;
-                uint32_t s = 0;
-                if (have) {
-                    const uint32_t code = sm.starts[l];       // chunk << 5 | flag bit 8*b + w  ->  byte 4*w + b of the chunk
-                    if (code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
-                }
-                bool to_detail = false;
-                if (have) {
-                    to_detail = true;
-                    if (!HAS_QUAL) {
-                        QuickLine q;
-                        PROF(9);
-                        const int st = quick_line(sm.buf, s, wlen, a.sites, cc, a.p, ALL, &q);
-                        PROF(10);
-                        if (st == ST_SKIP) to_detail = false;
-                        else if (st == ST_OK && !(q.end == wlen && !eof)) {   // (a line that leaves the window goes on)
-                            const uint16_t v = k1_cell(a, q.base, q.fail, q.site, base + s);
-                            if (buffered) res[line_idx] = v;
-                            else if (slot0 + line_idx < a.line_out_cap) a.line_out[slot0 + line_idx] = v;
-                            n_parsed++;
-                            to_detail = false;
-                        }
-                    }
-                }
-                if (buffered && to_detail) res[line_idx] = 0xffffu;   // emitted from the queue, not by flush_pending
-                uint32_t len_hint = 0;                        // up to the '\n' in front of the next listed start
+                if (buffered && to_detail) res[line_idx] = 0xffffu;       // emitted from the queue, not by flush_pending
+                uint32_t len_hint = 0;
                 if (to_detail && l + 1u < n_pass) {
-                    const uint32_t c1 = sm.starts[l + 1u];
+                    const uint32_t c1 = sm.starts[l + 1u] & START_CODE;
                     len_hint = (c1 >> 5) * 16u + (c1 & 7u) * 4u + ((c1 >> 3) & 3u) - s;
                 }
                 const unsigned long long entry = k1_entry(line_idx, len_hint, base + s);
-                PROF(11);
                 n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
                 if (n_dq >= 32u) {                            // leaves both queues below 32
                     drained = true;
@@ -665,10 +756,52 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                     const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
                     n_dq = r & 0xffffu; n_gq = r >> 16;
                 }
+            };
+            if (done + n_pass == n_tile_lines) {              // the tile's last pass: the next ticket, its latency hidden
+                if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);   // behind the parse
+                ticket_taken = true;
+            }
+            for (uint32_t l0 = 0; l0 < n_pass; l0 += use_helper ? 64u : 32u) {
+                const bool have = l0 + (uint32_t)lane < n_pass;
+                const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
+                const uint32_t code = have ? sm.starts[l] : 0u;
+                uint32_t s = 0;
+                bool to_detail;
+                PROF(9);
+                if (!HAS_QUAL) {
+                    to_detail = k1_quick_step<ALL>(a, sm, cc, ps, have, l, code, s, n_parsed);
+                } else {
+                    if (have && code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
+                    to_detail = have;
+                }
+                PROF(10);
+                queue_line(to_detail, l, s);
+                PROF(11);
+            }
+            if (use_helper) {
+                pair_sync(warp);                              // the helper is done with the window
+                const uint32_t declined = sm.h_declined;
+                if (declined) {                               // lines its first tier declined: marked in starts[]
+                    for (uint32_t l00 = 0; l00 < n_pass; l00 += 32u) {
+                        const uint32_t l = l00 + (uint32_t)lane;
+                        const uint32_t code = l < n_pass ? sm.starts[l] : 0u;
+                        const bool want = code == 0xffffu ? (declined & H_DECLINED_FIRST) != 0u : (code & START_MARK) != 0u;
+                        uint32_t s = 0;
+                        if (want && code != 0xffffu) {
+                            const uint32_t c = code & START_CODE;
+                            s = (c >> 5) * 16u + (c & 7u) * 4u + ((c >> 3) & 3u) + 1u;
+                        }
+                        queue_line(want, l, s);
+                    }
+                }
             }
         }
         PROF(12);
         n_lines += n_tile_lines;
+    }
+    if (K1_HELPER && !HAS_QUAL) {                             // out of tiles: the helper may leave
+        if (lane == 0) sm.h_flags = H_EXIT;
+        pair_sync(warp);
     }
     {
         PROF(0);

@@ -94,6 +94,17 @@ SNP_HD void contig_cache_load(const SiteTable &t, int cid, uint32_t *name4_store
     cc->len1 = L; cc->nblk = (nw + 3u) >> 2; cc->max_pos = t.max_pos[cid]; cc->bit_base = t.bit_base[cid];
 }
 
+// the register half of contig_cache_load: for a second warp that shares the first one's name4 / mask4 words
+SNP_HD void contig_cache_attach(const SiteTable &t, int cid, const uint32_t *name4_store, const uint32_t *mask4_store,
+                                uint32_t store_words, ContigCache *cc) {
+    cc->name4 = name4_store; cc->mask4 = mask4_store; cc->len1 = 0; cc->nblk = 0; cc->cid = cid; cc->max_pos = -1;
+    cc->bit_base = 0;
+    if (cid < 0 || cid >= t.n_contigs) return;
+    const uint32_t L = (uint32_t)t.len1[cid], nw = (L + 3u) >> 2;
+    if (nw > store_words) return;
+    cc->len1 = L; cc->nblk = (nw + 3u) >> 2; cc->max_pos = t.max_pos[cid]; cc->bit_base = t.bit_base[cid];
+}
+
 struct Word4 { uint32_t x, y, z, w; };
 SNP_HD Word4 load_word4(const uint32_t *p) {                  // p 16-byte aligned
 #if defined(__CUDA_ARCH__)
