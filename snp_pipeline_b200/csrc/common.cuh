@@ -26,7 +26,7 @@ struct PileupStatusDev {
 #ifndef K1_CFG_CHUNKS          // (tuning builds override these four on the nvcc command line)
 #define K1_CFG_CHUNKS 21
 #define K1_CFG_CTAS 4
-#define K1_CFG_LHCAP 11
+#define K1_CFG_LHCAP 10
 #define K1_CFG_QCAP 64
 #endif
 #ifndef K1_CFG_HELPER
@@ -35,18 +35,17 @@ struct PileupStatusDev {
 constexpr int K1_LANE_CHUNKS = K1_CFG_CHUNKS;             // 16-byte chunks one lane scans for newlines ...
 constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
 constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
-constexpr int K1_LOOK     = 1024;              // extra bytes staged so that the last owned line is complete
+constexpr int K1_LOOK     = 896;               // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
 constexpr int K1_WARPS    = 4;                 // independent pipelines per CTA: a leader warp each ...
 constexpr int K1_HELPER   = K1_CFG_HELPER;     // ... plus (1) a helper warp that parses every other group of 32 lines.
                                                // Off: at the 64 registers 32 warps per SM leave, the leader spills to L2 (measured -45 %)
 constexpr int K1_THREADS  = 32 * K1_WARPS * (1 + K1_HELPER);
 constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
-constexpr int K1_WCAP     = 256;               // line starts a warp lists per pass (more -> another pass)
+constexpr int K1_WCAP     = 192;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)
-constexpr int K1_RES_OFF  = 160;               // lanehits[K1_RES_OFF ..]: a parsed tile's per-line results (in front of it:
-                                               // the length sort's permutation and histogram, see k1_pileup.cu)
-constexpr int K1_RES_CAP  = 32 * K1_LHCAP - K1_RES_OFF;   // lines per tile that fit there (more -> written directly)
+constexpr int K1_RES_CAP  = 160;               // per-line results of a parsed tile kept in shared memory (K1Warp::res) until its first
+                                               // line's file-order index is known; tiles with more lines write theirs directly
 constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
 constexpr int K1_DRAIN_AT = 24;                // queued lines that trigger a drain between two tiles (32: also inside a tile)
 constexpr int K1_QCAP     = K1_CFG_QCAP;                // per-warp queue slots (drained whenever 32 are filled)

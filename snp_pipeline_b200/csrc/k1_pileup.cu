@@ -43,7 +43,9 @@ namespace snpgpu {
 struct K1Warp {                                 // one warp's slice of shared memory
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
     uint16_t starts[K1_WCAP];                   // line starts of the current pass, file order: chunk << 5 | flag bit
-    uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
+    uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane;
+                                                // afterwards the length sort's permutation and histogram
+    uint16_t res[K1_RES_CAP];                   // per-line results of the tile parsed last, until they can be stored in file order
     alignas(16) uint32_t cname[K1_NAMEW];       // name + tab of the contig the warp expects (ContigCache::name4) ...
     alignas(16) uint32_t cmask[K1_NAMEW];       // ... and which of its bytes count (ContigCache::mask4)
     unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh (k1_entry)
@@ -72,6 +74,7 @@ __device__ __forceinline__ void pair_sync(int pipe) {          // (immediate bar
 }
 
 static_assert(K1_PAD >= (int)QUICK_PAD && K1_NAMEW % 4 == 0, "line_quick.cuh preconditions");
+static_assert(K1_WCAP <= 256 && K1_WCAP + 64 <= 2 * 32 * K1_LHCAP, "permutation (one byte per line) + histogram fit in lanehits");
 static_assert(sizeof(K1Warp) * K1_WARPS * K1_CTAS_PER_SM + 1024 * K1_CTAS_PER_SM <= 228 * 1024, "shared memory per SM");
 size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
 
@@ -159,7 +162,15 @@ __device__ __forceinline__ void k1_tile_publish(const PileupArgs &a, int tile, u
     st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n;
 }
 
-__device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane) {
+// the look-back's first window for `tile`, asked for ahead of time (k1_tile_resolve's `early`): lane L's view of tile - 1 - L
+__device__ __forceinline__ unsigned long long k1_tile_peek(const PileupArgs &a, int tile, int lane) {
+    volatile unsigned long long *st = a.tile_state;
+    const int t = tile - 1 - lane;
+    return t >= 0 ? st[t] : (2ull << 62);
+}
+
+__device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane,
+                                                              unsigned long long early = 0ull) {
     volatile unsigned long long *st = a.tile_state;
     const unsigned long long UPTO = 2ull << 62, VAL = (1ull << 62) - 1ull;
     unsigned long long before = 0;
@@ -168,7 +179,7 @@ __device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &
             const int t = j - lane;
             unsigned long long v = UPTO;                      // in front of tile 0: nothing
             if (t >= 0) {
-                v = st[t];
+                v = j == tile - 1 && (early >> 62) != 0ull ? early : st[t];      // (an early view is as good as a late one)
                 while ((v >> 62) == 0ull) { __nanosleep(100); v = st[t]; }
             }
             const uint32_t upto = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
@@ -411,7 +422,7 @@ struct K1Pass {
 template <bool ALL>
 __device__ __forceinline__ bool k1_quick_step(const PileupArgs &a, K1Warp &sm, const ContigCache &cc, const K1Pass &ps,
                                               bool have, uint32_t l, uint32_t code, uint32_t &s, uint32_t &n_parsed) {
-    uint16_t *res = sm.lanehits + K1_RES_OFF;
+    uint16_t *res = sm.res;
     const uint32_t line_idx = ps.done + l;
     s = 0;                                                    // code: chunk << 5 | flag bit 8*b + w  ->  byte 4*w + b of the chunk
     if (have && code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
@@ -512,13 +523,18 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     __syncwarp();
     // Per-line results of the tile just parsed wait in shared memory (the tail of lanehits) until the file-order
     // index of the tile's first line is known -- resolved one tile later, while the next window is in flight.
-    uint16_t *res = sm.lanehits + K1_RES_OFF;
+    uint16_t *res = sm.res;
     int pend_tile = -1;                                       // tile whose results sit in res
     uint32_t pend_n = 0;
     bool pend_known = false;
     unsigned long long pend_first = 0;
+    unsigned long long pend_early = 0;                        // this lane's early view of the look-back window (0: none)
     auto resolve_pending = [&]() {                            // (needed before any queued line of that tile is emitted)
-        if (pend_tile >= 0 && !pend_known) { pend_first = k1_tile_resolve(a, pend_tile, pend_n, lane); pend_known = true; }
+        if (pend_tile >= 0 && !pend_known) {
+            pend_first = k1_tile_resolve(a, pend_tile, pend_n, lane, pend_early);
+            pend_known = true;
+        }
+        pend_early = 0;
     };
     auto flush_pending = [&]() {
         if (pend_tile < 0) return;
@@ -574,9 +590,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         PROF(1);
-        flush_pending();                                      // the previous tile's results, while this window loads
+        // the previous tile's results are stored after this window's scan; the look-back they need is asked for now, so
+        // that its trip to L2 hides behind the window's arrival and the scan
+        if (pend_tile >= 0 && !pend_known) pend_early = k1_tile_peek(a, pend_tile, lane);
         PROF(2);
-        if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines too: every tile they belong to is resolved now
+        if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines: every tile they belong to must be resolved first
+            flush_pending();
             drained = true;
             const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
             n_dq = r & 0xffffu; n_gq = r >> 16;
@@ -662,6 +681,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         unsigned long long slot0 = ~0ull - 0xffffull;
         if (a.line_out) {
             if (lane == 0) k1_tile_publish(a, tile, n_tile_lines);
+            flush_pending();                                  // the previous tile's results leave sm.res
             if (n_tile_lines <= (uint32_t)K1_RES_CAP) {
                 buffered = true;
                 pend_tile = tile; pend_n = n_tile_lines; pend_known = false;
@@ -679,7 +699,6 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 if (idx < (uint32_t)K1_WCAP) sm.starts[idx] = myhits[k];
             }
         }
-        if (buffered) __syncwarp();                           // (res overlays the lane lists just copied)
         PROF(7);
         // ---- parse, K1_WCAP lines per pass -------------------------------------------------------------
         for (uint32_t done = 0; done < n_tile_lines; done += K1_WCAP) {
