@@ -203,14 +203,25 @@ def host_step(w, pool, pool_n, bufs, dist=None, world=1):
     sites = build_sites(ctx, uniq)
     n_sites = uniq.size
     rows, lines, stats = bufs
-    for i in range(w.n):
-        k = i % len(pool)
-        rc = ctx.lib.snpgpu_pileup_consensus(ctx.handle, ctypes.c_void_p(pool[k].ctypes.data), pool_n[k], sites.handle,
-                                             ctypes.byref(w.params), lib.MODE_ALL, ctypes.c_void_p(rows[i].ctypes.data),
-                                             ctypes.c_void_p(lines.ctypes.data), lines.size, ctypes.byref(stats))
-        ctx._check(rc)
-        h2d += pool_n[k]
-        d2h += n_sites + 2 * stats.n_lines + ctypes.sizeof(stats)
+    # one call kept ahead (snpgpu_pileup_consensus_begin / _end): sample i+1's text crosses PCIe while sample i's
+    # kernels run and its results come back
+    in_flight = None
+    for i in range(w.n + 1):
+        nxt = None
+        if i < w.n:
+            k = i % len(pool)
+            slot = ctypes.c_int(-1)
+            rc = ctx.lib.snpgpu_pileup_consensus_begin(
+                ctx.handle, ctypes.c_void_p(pool[k].ctypes.data), pool_n[k], sites.handle, ctypes.byref(w.params),
+                lib.MODE_ALL, ctypes.c_void_p(rows[i].ctypes.data), ctypes.c_void_p(lines[i % 2].ctypes.data),
+                lines[i % 2].size, ctypes.byref(stats[i % 2]), ctypes.byref(slot))
+            ctx._check(rc)
+            h2d += pool_n[k]
+            nxt = (slot.value, i % 2)
+        if in_flight is not None:
+            ctx._check(ctx.lib.snpgpu_pileup_consensus_end(ctx.handle, in_flight[0]))
+            d2h += n_sites + 2 * stats[in_flight[1]].n_lines + ctypes.sizeof(stats[0])
+        in_flight = nxt
     m = rows[:, :n_sites]
     if world == 1:
         d = np.zeros((w.n, w.n), dtype=np.int32)
@@ -428,8 +439,8 @@ def main():
             pool.append(arr); pool_n.append(w.nbytes[k]); owners.append(owner)
         rows_arr, rows_owner = ctx.pinned_array(w.n * ((n_sites + 63) // 64 * 64 + 64))
         rows = rows_arr.reshape(w.n, -1)
-        lines_arr, lines_owner = ctx.pinned_array(2 * (args.genome_len + 64))
-        bufs = (rows, lines_arr.view(np.uint16), _lib.PileupStats())
+        lines_arr, lines_owner = ctx.pinned_array(2 * 2 * (args.genome_len + 64))
+        bufs = (rows, lines_arr.view(np.uint16).reshape(2, -1), (_lib.PileupStats(), _lib.PileupStats()))
         for _ in range(max(1, min(args.warmup, 1))):
             m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs, dist, world)
         barrier()

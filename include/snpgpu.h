@@ -134,6 +134,18 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes,
                             uint8_t *row_out, uint16_t *line_out, size_t line_out_cap,
                             snpgpu_pileup_stats *stats);
 
+/* The same call in two halves, for callers that stream many samples (the reference runs one call_consensus process per
+ * sample, run.py:709-710): _begin enqueues the copy in, the kernels and the copies out on one of the context's two
+ * internal lanes and returns at once; _end waits for that call and reports exactly like snpgpu_pileup_consensus.
+ * Keeping one call ahead lets the next sample's text cross PCIe while this sample's kernels run and its results go
+ * back.  At most two calls in flight; text / row_out / line_out / stats must stay valid until _end and should be
+ * page-locked (snpgpu_host_alloc), pageable memory makes the copies synchronous.  snpgpu_pileup_vcf_records does not
+ * apply to pipelined calls. */
+int snpgpu_pileup_consensus_begin(snpgpu_ctx *ctx, const void *text, size_t nbytes, const snpgpu_sites *sites,
+                                  const snpgpu_params *params, int mode, uint8_t *row_out, uint16_t *line_out,
+                                  size_t line_out_cap, snpgpu_pileup_stats *stats, int *slot_out);
+int snpgpu_pileup_consensus_end(snpgpu_ctx *ctx, int slot);
+
 /* text already in device memory (16-byte aligned).  row_out_dev: n_snp bytes.  line_out_dev: nullable,
  * one uint16 per line in file order, capacity line_out_cap.  stats_dev: nullable device copy of
  * snpgpu_pileup_stats (valid after the stream is synchronised).  Nothing is synchronised here. */

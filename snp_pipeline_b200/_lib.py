@@ -23,6 +23,7 @@ EXPORTS = [
     "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_enable_timing",
     "snpgpu_kernel_time", "snpgpu_sites_create", "snpgpu_sites_create_from_keys_dev",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
+    "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end",
     "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
@@ -119,6 +120,10 @@ def load():
     L.snpgpu_sites_n_snp.argtypes = [vp]
     L.snpgpu_pileup_consensus.restype = ctypes.c_int
     L.snpgpu_pileup_consensus.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, P(PileupStats)]
+    L.snpgpu_pileup_consensus_begin.restype = ctypes.c_int
+    L.snpgpu_pileup_consensus_begin.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, vp, P(ctypes.c_int)]
+    L.snpgpu_pileup_consensus_end.restype = ctypes.c_int
+    L.snpgpu_pileup_consensus_end.argtypes = [vp, ctypes.c_int]
     L.snpgpu_pileup_consensus_dev.restype = ctypes.c_int
     L.snpgpu_pileup_consensus_dev.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, vp]
     L.snpgpu_normalize_newlines_dev.restype = ctypes.c_int
@@ -328,6 +333,21 @@ class Context(object):
             self._check(rc)
             return rec[:n_rec.value], alt[:n_alt.value]
         raise SnpGpuError(E_NOMEM, "pileup_vcf_records: capacities kept growing")
+
+    def pileup_consensus_begin(self, text, sites, params, mode, row_out, line_out=None, stats=None):
+        """First half of the pipelined host-buffer call (snpgpu_pileup_consensus_begin): text / row_out / line_out are
+        numpy arrays (page-locked ones from pinned_array() for real overlap), stats a PileupStats; all must stay alive
+        until pileup_consensus_end(slot).  Returns the slot."""
+        slot = ctypes.c_int(-1)
+        rc = self.lib.snpgpu_pileup_consensus_begin(
+            self.handle, _np_ptr(text), text.size, sites.handle, ctypes.byref(params), mode, _np_ptr(row_out),
+            _np_ptr(line_out) if line_out is not None else None, line_out.size if line_out is not None else 0,
+            ctypes.byref(stats) if stats is not None else None, ctypes.byref(slot))
+        self._check(rc)
+        return slot.value
+
+    def pileup_consensus_end(self, slot):
+        self._check(self.lib.snpgpu_pileup_consensus_end(self.handle, slot))
 
     def pileup_consensus_dev(self, text_ptr, nbytes, sites, params, mode, row_ptr, line_ptr=0, line_cap=0,
                              stats_ptr=0):

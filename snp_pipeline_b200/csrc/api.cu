@@ -48,6 +48,18 @@ struct snpgpu_ctx {
     DevBuf k4_tmp, k4_mat, k4_dist;
     DevBuf synth_tmp, synth_n;
     DevBuf k3_tmp;
+    // pipelined host-buffer calls (snpgpu_pileup_consensus_begin / _end): two child contexts, each with its own stream,
+    // staging buffers and kernel scratch, so that one call's copy in overlaps the other's kernels and copies out
+    struct Pending {
+        bool active = false;
+        const void *text = nullptr; size_t nbytes = 0; const snpgpu_sites *sites = nullptr; snpgpu_params params;
+        int mode = 0; uint8_t *row_out = nullptr; uint16_t *line_out = nullptr; size_t line_out_cap = 0;
+        snpgpu_pileup_stats *stats = nullptr;
+    };
+    snpgpu_ctx *lane[2] = {nullptr, nullptr};
+    Pending pending[2];
+    snpgpu_pileup_stats *lane_stats[2] = {nullptr, nullptr};   // pinned
+    cudaEvent_t lane_event = nullptr;
     std::vector<std::pair<void *, size_t>> sites_pool;   // blobs of destroyed device-built site tables, reused in stream order
     size_t arena_want = 1 << 20;
     bool   timing = false;
@@ -128,6 +140,11 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->lane[k]) snpgpu_destroy(ctx->lane[k]);
+        if (ctx->lane_stats[k]) cudaFreeHost(ctx->lane_stats[k]);
+    }
+    if (ctx->lane_event) cudaEventDestroy(ctx->lane_event);
     DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->arena,
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
                      &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
@@ -466,6 +483,84 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
         return SNPGPU_OK;
     }
     return fail(ctx, SNPGPU_E_NOMEM, "pileup_consensus: splice scratch");
+}
+
+// ---- the same call, pipelined: _begin enqueues copy in + kernels + copies out on one of two lanes and returns,
+//      _end waits for that call and reports like snpgpu_pileup_consensus.  A caller that streams samples keeps one call
+//      ahead: the next sample's text crosses PCIe while this sample's kernels run and its results go back.
+int snpgpu_pileup_consensus_begin(snpgpu_ctx *ctx, const void *text, size_t nbytes, const snpgpu_sites *sites,
+                                  const snpgpu_params *params, int mode, uint8_t *row_out, uint16_t *line_out,
+                                  size_t line_out_cap, snpgpu_pileup_stats *stats, int *slot_out) {
+    if (!ctx || !sites || !params || !slot_out || (nbytes && !text))
+        return fail(ctx, SNPGPU_E_ARG, "pileup_consensus_begin: null argument");
+    if (sites->n_snp && !row_out) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus_begin: row_out is null");
+    int k = !ctx->pending[0].active ? 0 : (!ctx->pending[1].active ? 1 : -1);
+    if (k < 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus_begin: two calls are already in flight");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->lane[k]) {
+        int rc = snpgpu_create(ctx->device, &ctx->lane[k]);
+        if (rc) return fail(ctx, rc, "pileup_consensus_begin: lane context");
+        CK(cudaHostAlloc((void **)&ctx->lane_stats[k], sizeof(snpgpu_pileup_stats), cudaHostAllocDefault));
+    }
+    if (!ctx->lane_event) CK(cudaEventCreateWithFlags(&ctx->lane_event, cudaEventDisableTiming));
+    snpgpu_ctx *L = ctx->lane[k];
+    cudaStream_t st = L->stream;
+    CK(cudaEventRecord(ctx->lane_event, ctx->stream));         // (a site table built in stream order on the parent is ready)
+    CK(cudaStreamWaitEvent(st, ctx->lane_event, 0));
+    const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
+    L->text_valid = false;
+    CK(L->text.ensure(nbytes + 64));
+    CK(L->row.ensure(sites->n_snp + 16));
+    CK(L->stats.ensure(sizeof(snpgpu_pileup_stats)));
+    if (want_lines) CK(L->lines.ensure(line_out_cap * sizeof(uint16_t)));
+    if (nbytes) CK(cudaMemcpyAsync(L->text.p, text, nbytes, cudaMemcpyHostToDevice, st));
+    int rc = snpgpu_pileup_consensus_dev(L, L->text.p, nbytes, sites, params, mode, (uint8_t *)L->row.p,
+                                         want_lines ? (uint16_t *)L->lines.p : nullptr, line_out_cap,
+                                         (snpgpu_pileup_stats *)L->stats.p);
+    if (rc) { ctx->err = L->err; return rc; }
+    CK(cudaMemcpyAsync(ctx->lane_stats[k], L->stats.p, sizeof(snpgpu_pileup_stats), cudaMemcpyDeviceToHost, st));
+    if (sites->n_snp) CK(cudaMemcpyAsync(row_out, L->row.p, sites->n_snp, cudaMemcpyDeviceToHost, st));
+    snpgpu_ctx::Pending &p = ctx->pending[k];
+    p.active = true; p.text = text; p.nbytes = nbytes; p.sites = sites; p.params = *params; p.mode = mode;
+    p.row_out = row_out; p.line_out = line_out; p.line_out_cap = line_out_cap; p.stats = stats;
+    *slot_out = k;
+    return SNPGPU_OK;
+}
+
+int snpgpu_pileup_consensus_end(snpgpu_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot > 1 || !ctx->pending[slot].active)
+        return fail(ctx, SNPGPU_E_ARG, "pileup_consensus_end: no such call in flight");
+    snpgpu_ctx::Pending p = ctx->pending[slot];
+    ctx->pending[slot].active = false;
+    snpgpu_ctx *L = ctx->lane[slot];
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(L->stream));
+    const snpgpu_pileup_stats hs = *ctx->lane_stats[slot];
+    ctx->launches += L->launches; L->launches = 0;
+    if (hs.error_code == SNPGPU_E_LONECR || hs.error_code == SNPGPU_E_NOMEM) {
+        // lone-CR line ends or a splice scratch that has to grow: the plain call knows how to redo the sample
+        int rc = snpgpu_pileup_consensus(L, p.text, p.nbytes, p.sites, &p.params, p.mode, p.row_out, p.line_out,
+                                         p.line_out_cap, p.stats);
+        ctx->launches += L->launches; L->launches = 0;
+        if (rc) ctx->err = L->err;
+        return rc;
+    }
+    const bool want_lines = p.mode == SNPGPU_MODE_ALL && p.line_out != nullptr && p.line_out_cap > 0;
+    if (want_lines && hs.error_code == 0) {
+        size_t n = (size_t)std::min<uint64_t>(hs.n_lines, p.line_out_cap);
+        if (n) {
+            CK(cudaMemcpyAsync(p.line_out, L->lines.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, L->stream));
+            CK(cudaStreamSynchronize(L->stream));
+        }
+    }
+    if (p.stats) *p.stats = hs;
+    if (hs.error_code) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "pileup_consensus: the reference raises (code %d) on the line at byte offset %llu",
+                 hs.error_code, (unsigned long long)hs.error_offset);
+        return fail(ctx, hs.error_code, msg);
+    }
+    return SNPGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------ K5

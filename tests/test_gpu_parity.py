@@ -300,6 +300,56 @@ def test_synthetic_sample_device_resident(ctx, genome_len, sample):
 
 
 # ------------------------------------------------------------------------------------------ K2
+def test_pipelined_host_calls(ctx):
+    """snpgpu_pileup_consensus_begin / _end with one call kept ahead: the same rows, per-line calls and stats as the plain
+    call, also when a sample needs the redo paths (classic-Mac line ends) or raises."""
+    from snp_pipeline_b200 import _lib
+    rng = random.Random(11)
+    n = 1500
+    snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 120))]
+    sites = ctx.sites(snps)
+    p = _lib.make_params(min_cons_depth=3)
+    texts = [linegen.pileup_text(60 + k, n).encode() for k in range(5)]
+    texts[2] = texts[2].replace(b"\n", b"\r")                               # lone CRs: normalised and redone inside _end
+    bad = texts[3].split(b"\n")
+    bad[700] = bad[700].replace(b"\t", b"\tx", 1).replace(b"\tx", b"\t", 0)
+    f = bad[700].split(b"\t"); f[1] = b"12x"; bad[700] = b"\t".join(f)     # int("12x") raises in the reference
+    texts[3] = b"\n".join(bad)
+    want = []
+    for t in texts:
+        try:
+            want.append(ctx.pileup_consensus(t, sites, p, _lib.MODE_ALL, want_lines=True))
+        except _lib.SnpGpuError as e:
+            want.append(e)
+    arrs = [np.frombuffer(t, dtype=np.uint8) for t in texts]
+    rows = [np.zeros(len(snps), np.uint8) for _ in texts]
+    lines = [np.zeros(n + 8, np.uint16) for _ in texts]
+    stats = [_lib.PileupStats() for _ in texts]
+    got_err = {}
+    prev = None
+    for k in range(len(texts) + 1):
+        cur = None
+        if k < len(texts):
+            cur = (ctx.pileup_consensus_begin(arrs[k], sites, p, _lib.MODE_ALL, rows[k], lines[k], stats[k]), k)
+        if prev is not None:
+            try:
+                ctx.pileup_consensus_end(prev[0])
+            except _lib.SnpGpuError as e:
+                got_err[prev[1]] = e
+        prev = cur
+    for k, w in enumerate(want):
+        if isinstance(w, _lib.SnpGpuError):
+            assert k in got_err and got_err[k].code == w.code and stats[k].error_offset == w.offset
+            continue
+        assert k not in got_err
+        assert rows[k].tobytes() == w[0]
+        assert stats[k].n_lines == w[1].n_lines and stats[k].n_parsed == w[1].n_parsed
+        assert np.array_equal(lines[k][:stats[k].n_lines], w[2])
+    with pytest.raises(_lib.SnpGpuError):
+        ctx.pileup_consensus_end(0)                                          # nothing in flight
+    sites.close()
+
+
 def test_site_table_built_on_device(ctx):
     """snpgpu_sites_create_from_keys_dev (K2's keys -> site table, no host round trip) against the host-built table:
     same consensus rows, same per-line calls, on two contigs."""
