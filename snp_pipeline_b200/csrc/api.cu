@@ -251,6 +251,7 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
     size_t s_bits = add(h.bits.data(), h.bits.size() * 4);
     size_t s_rank = add(h.rank.data(), h.rank.size() * 4);
     size_t s_flags = add(h.flags.data(), h.flags.size());
+    size_t s_words = add(h.words.data(), h.words.size() * sizeof(SiteWord));
     size_t s_su = add(h.snp_unique.data(), h.snp_unique.size() * 4);
     snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
     if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create: host allocation");
@@ -271,6 +272,7 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
     s->table.name_off = (const int32_t *)at(s_noff); s->table.bit_base = (const int64_t *)at(s_base);
     s->table.max_pos = (const int64_t *)at(s_max); s->table.bits = (const uint32_t *)at(s_bits);
     s->table.rank = (const uint32_t *)at(s_rank); s->table.flags = (const uint8_t *)at(s_flags);
+    s->table.words = (const SiteWord *)at(s_words);
     s->snp_unique = (int32_t *)at(s_su);
     *out = s;
     return SNPGPU_OK;
@@ -330,7 +332,8 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
     const size_t small = stage.size();
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_bits = small, o_rank = o_bits + up(n_words * 4), o_flags = o_rank + up(n_words * 4);
-    const size_t o_su = o_flags + up(n_keys + 1), total = o_su + up((n_keys + 1) * 4);
+    const size_t o_su = o_flags + up(n_keys + 1), o_words = o_su + up((n_keys + 1) * 4);
+    const size_t total = o_words + up(n_words * sizeof(SiteWord));
     snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
     if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create_from_keys_dev: host allocation");
     for (size_t k = 0; k < ctx->sites_pool.size(); k++) {
@@ -354,7 +357,7 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
     if (e == cudaSuccess)
         launched = k3_launch(ctx->stream, (const unsigned long long *)keys_dev, n_keys, n_contigs, (const int64_t *)at(o_base),
                              (const int64_t *)at(o_max), (uint32_t *)at(o_bits), (uint32_t *)at(o_rank), n_words,
-                             at(o_flags), (int32_t *)at(o_su), ctx->k3_tmp.p, ctx->k3_tmp.cap);
+                             at(o_flags), (int32_t *)at(o_su), (SiteWord *)at(o_words), ctx->k3_tmp.p, ctx->k3_tmp.cap);
     if (e != cudaSuccess || launched < 0) {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(s->blob); delete s;
@@ -368,6 +371,7 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
     s->table.name_off = (const int32_t *)at(o_noff); s->table.bit_base = (const int64_t *)at(o_base);
     s->table.max_pos = (const int64_t *)at(o_max); s->table.bits = (const uint32_t *)at(o_bits);
     s->table.rank = (const uint32_t *)at(o_rank); s->table.flags = at(o_flags);
+    s->table.words = (const SiteWord *)at(o_words);
     s->snp_unique = (int32_t *)at(o_su);
     *out = s;
     return SNPGPU_OK;

@@ -63,6 +63,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
             st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
             if (st == ST_OK) {
                 if (q.end != e) { counters[3] = s; counters[4] = 99; break; }   // harness self-check: the line end
+                if (q.flags != (q.site >= 0 ? h.flags[q.site] : 0)) { counters[3] = s; counters[4] = 98; break; }   // ... and the site's flags
                 fl.base = q.base; fl.fail = q.fail; fl.site = q.site;
                 n_quick++;
             }

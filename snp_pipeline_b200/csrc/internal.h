@@ -25,7 +25,7 @@ int    k5_launch_tally(cudaStream_t stream, const uint8_t *text, size_t nbytes, 
 size_t k3_scan_bytes(size_t n_words);
 int    k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
                  const int64_t *max_pos, uint32_t *bits, uint32_t *rank, size_t n_words, uint8_t *flags,
-                 int32_t *snp_unique, void *tmp, size_t tmp_bytes);
+                 int32_t *snp_unique, SiteWord *words, void *tmp, size_t tmp_bytes);
 
 // k2_merge.cu
 // sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller

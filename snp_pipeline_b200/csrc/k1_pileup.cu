@@ -121,9 +121,15 @@ __device__ __forceinline__ void k1_report(const PileupArgs &a, unsigned long lon
 
 // call_consensus.py:165-176: Region failure, '-' substitution, keep the cell for the snplist gather.
 // Returns the line's result word: matrix cell | fail mask << 8.
+__device__ __forceinline__ uint16_t k1_cell_flags(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                                  unsigned flags, unsigned long long goff);
 __device__ __forceinline__ uint16_t k1_cell(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
                                             unsigned long long goff) {
-    unsigned flags = site >= 0 ? a.sites.flags[site] : 0u;
+    return k1_cell_flags(a, base_ch, fail, site, site >= 0 ? a.sites.flags[site] : 0u, goff);
+}
+// (flags: SITE_* of the site, 0 when the line is at none)
+__device__ __forceinline__ uint16_t k1_cell_flags(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                                  unsigned flags, unsigned long long goff) {
     if (flags & SITE_EXCLUDED) fail |= FAIL_REGION;
     unsigned cell = (fail || base_ch == '*') ? (unsigned)'-' : base_ch;
     if (flags & SITE_SNP) atomicMax(&a.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
@@ -433,7 +439,7 @@ __device__ __forceinline__ bool k1_quick_step(const PileupArgs &a, K1Warp &sm, c
         const int st = quick_line(sm.buf, s, ps.wlen, a.sites, cc, a.p, ALL, &q);
         if (st == ST_SKIP) to_detail = false;
         else if (st == ST_OK && !(q.end == ps.wlen && !ps.eof)) {     // (a line that leaves the window goes on)
-            const uint16_t v = k1_cell(a, q.base, q.fail, q.site, ps.base + s);
+            const uint16_t v = k1_cell_flags(a, q.base, q.fail, q.site, q.flags, ps.base + s);
             if (ps.buffered) res[line_idx] = v;
             else if (ps.slot0 + line_idx < a.line_out_cap) a.line_out[ps.slot0 + line_idx] = v;
             n_parsed++;

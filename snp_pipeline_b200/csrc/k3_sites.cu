@@ -37,6 +37,12 @@ struct PopcOp {
     }
 };
 
+// bits + rank -> the packed words of the first-tier parser (every site is a snplist entry, none is excluded)
+__global__ void k3_pack_words_kernel(const uint32_t *bits, const uint32_t *rank, size_t n_words, SiteWord *words) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_words) words[w] = SiteWord{bits[w], bits[w], 0u, rank[w]};
+}
+
 size_t k3_scan_bytes(size_t n_words) {
     size_t b = 0;
     cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(nullptr, PopcOp());
@@ -47,7 +53,7 @@ size_t k3_scan_bytes(size_t n_words) {
 // bits / rank: n_words words each, bits zeroed here; returns the number of kernels launched, or < 0
 int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
               const int64_t *max_pos, uint32_t *bits, uint32_t *rank, size_t n_words, uint8_t *flags,
-              int32_t *snp_unique, void *tmp, size_t tmp_bytes) {
+              int32_t *snp_unique, SiteWord *words, void *tmp, size_t tmp_bytes) {
     if (cudaMemsetAsync(bits, 0, n_words * sizeof(uint32_t), stream) != cudaSuccess) return -1;
     int launches = 0;
     if (n) {
@@ -57,7 +63,8 @@ int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int
     }
     cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(bits, PopcOp());
     if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, rank, (int64_t)n_words, stream) != cudaSuccess) return -1;
-    return launches + 2;
+    k3_pack_words_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(bits, rank, n_words, words);
+    return launches + 3;
 }
 
 }  // namespace snpgpu

@@ -27,6 +27,7 @@ struct QuickLine {
     uint32_t end;          // offset of the line terminator in buf
     uint8_t  base;         // consensus character before the '-' substitutions of call_consensus.py:169-176
     uint8_t  fail;         // FAIL_* mask (without FAIL_REGION)
+    uint8_t  flags;        // SITE_SNP / SITE_EXCLUDED of the site
 };
 
 // acc + 128 * (number of bytes of `flags` that are 0x80); flags holds 0x80 / 0x00 bytes only
@@ -105,6 +106,15 @@ SNP_HD void contig_cache_attach(const SiteTable &t, int cid, const uint32_t *nam
     cc->len1 = L; cc->nblk = (nw + 3u) >> 2; cc->max_pos = t.max_pos[cid]; cc->bit_base = t.bit_base[cid];
 }
 
+SNP_HD SiteWord load_site_word(const SiteWord *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return SiteWord{v.x, v.y, v.z, v.w};
+#else
+    return *p;
+#endif
+}
+
 struct Word4 { uint32_t x, y, z, w; };
 SNP_HD Word4 load_word4(const uint32_t *p) {                  // p 16-byte aligned
 #if defined(__CUDA_ARCH__)
@@ -180,11 +190,19 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     bad |= buf[i] != '\t';
     i++;
     if (bad) return ST_DETAIL;
-    // site_find (sites.cuh) on the cached contig: the bitmap word is asked for here; in all-positions mode it is only
-    // looked at when the line is done, so its latency hides behind the rest of the parse
+    // site_find (sites.cuh) on the cached contig: the packed word of the position's 32-position group is asked for here
+    // (one 16-byte load: site bits, snplist / exclude bits, rank); in all-positions mode it is only looked at when the
+    // line is done, so its latency hides behind the rest of the parse and nothing else has to be loaded for the site
     const int64_t bit = cc.bit_base + (int64_t)pos;
-    const uint32_t bw = (int64_t)pos <= cc.max_pos ? sites.bits[bit >> 5] : 0u, bb = (uint32_t)bit & 31u;
-    if (!all_positions && !((bw >> bb) & 1u)) return ST_SKIP;
+    const uint32_t bb = (uint32_t)bit & 31u;
+    SiteWord sw{0u, 0u, 0u, 0u};
+    if (all_positions) {
+        if ((int64_t)pos <= cc.max_pos) sw = load_site_word(sites.words + (bit >> 5));
+    } else {                                           // filter mode: the plain bitmap decides, nearly always "skip"
+        const uint32_t bw = (int64_t)pos <= cc.max_pos ? sites.bits[bit >> 5] : 0u;
+        if (!((bw >> bb) & 1u)) return ST_SKIP;
+        sw = load_site_word(sites.words + (bit >> 5));
+    }
     const unsigned ref = buf[i];
     bad = ((ref | 0x20u) - 'a') >= 26u;                // a letter: '.'/',' stand for REF / ref (pileup.py:255-256)
     bad |= buf[i + 1] != '\t';
@@ -257,7 +275,8 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     // ---- call (pileup.py:550-588): the reference base wins outright ---------------------------------
     const uint32_t dc = a_dc >> 7, dot = a_dot >> 7;
     if (dc <= nb - dc) return ST_DETAIL;
-    out->site = ((bw >> bb) & 1u) ? (int32_t)(sites.rank[bit >> 5] + (uint32_t)popc32(bw & ((1u << bb) - 1u))) : -1;
+    out->site = ((sw.any >> bb) & 1u) ? (int32_t)(sw.rank + (uint32_t)popc32(sw.any & ((1u << bb) - 1u))) : -1;
+    out->flags = (uint8_t)((((sw.snp >> bb) & 1u) ? SITE_SNP : 0u) | (((sw.exc >> bb) & 1u) ? SITE_EXCLUDED : 0u));
     out->end = q0 + nb;
     out->base = (uint8_t)ref;
     out->fail = filter_mask(nb, dc, dot, dc - dot, p);

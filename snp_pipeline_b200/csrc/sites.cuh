@@ -13,6 +13,10 @@ namespace snpgpu {
 
 enum : uint8_t { SITE_SNP = 1, SITE_EXCLUDED = 2 };
 
+// what the first-tier parser wants to know about 32 positions, in one 16-byte load: which are sites, which of those are
+// in the snplist / in the exclude file, and how many sites lie in front of the word
+struct SiteWord { uint32_t any, snp, exc, rank; };
+
 struct SiteTable {
     int32_t         n_contigs;
     int32_t         n_unique;
@@ -26,6 +30,7 @@ struct SiteTable {
     const uint32_t *bits;
     const uint32_t *rank;
     const uint8_t  *flags;      // n_unique
+    const SiteWord *words;      // the same facts packed per bitmap word (bits / flags / rank remain for the other tiers)
 };
 
 // index of (contig, pos) among the unique sites, or -1

@@ -18,6 +18,7 @@ struct HostSites {
     std::vector<int64_t>  bit_base, max_pos;
     std::vector<uint32_t> bits, rank;
     std::vector<uint8_t>  flags;
+    std::vector<SiteWord> words;
     std::vector<int32_t>  snp_unique;       // unique-site index of snplist entry k
 
     SiteTable view() const {
@@ -26,7 +27,7 @@ struct HostSites {
         t.names4 = names4.data(); t.off4 = off4.data(); t.len1 = len1.data();
         t.names = names.data(); t.name_off = name_off.data();
         t.bit_base = bit_base.data(); t.max_pos = max_pos.data();
-        t.bits = bits.data(); t.rank = rank.data(); t.flags = flags.data();
+        t.bits = bits.data(); t.rank = rank.data(); t.flags = flags.data(); t.words = words.data();
         return t;
     }
 };
@@ -88,6 +89,13 @@ inline int build_host_sites(const char *contig_names, const int32_t *name_off, i
     };
     for (size_t i = 0; i < n_snp; i++) { size_t u = find(snp_contig[i], snp_pos[i]); h.flags[u] |= SITE_SNP; h.snp_unique[i] = (int32_t)u; }
     for (size_t i = 0; i < n_exc; i++) h.flags[find(exc_contig[i], exc_pos[i])] |= SITE_EXCLUDED;
+    h.words.assign(n_words, SiteWord{0u, 0u, 0u, 0u});
+    for (size_t w = 0; w < n_words; w++) { h.words[w].any = h.bits[w]; h.words[w].rank = h.rank[w]; }
+    for (size_t u = 0; u < keys.size(); u++) {
+        const int64_t b = h.bit_base[keys[u].c] + keys[u].p;
+        if (h.flags[u] & SITE_SNP) h.words[b >> 5].snp |= 1u << (b & 31);
+        if (h.flags[u] & SITE_EXCLUDED) h.words[b >> 5].exc |= 1u << (b & 31);
+    }
     // padded contig entries: name + '\t', zero-filled to whole words
     h.off4.assign((size_t)n_contigs + 1, 0);
     h.len1.assign(nc1, 0);
