@@ -106,6 +106,14 @@ int  snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names
 void snpgpu_sites_destroy(snpgpu_sites *sites);
 size_t snpgpu_sites_n_snp(const snpgpu_sites *sites);
 
+/* ---- Reference bases at the snplist positions.  Replaces the gather of utils.write_reference_snp_file
+ *      (utils.py:1100-1108: match_dict[id][int(pos) - 1].upper() per snplist entry of that contig).
+ *      out[k] = upper(seq[pos[k] - 1]) with Python's indexing (position 0 and negative positions count from the
+ *      end); a position outside the sequence -> SNPGPU_E_INDEX (the reference's IndexError), *bad_index = the
+ *      first such k.  Host buffers; copies inside the call. ------------------------------------------------ */
+int snpgpu_reference_bases(snpgpu_ctx *ctx, const uint8_t *seq, size_t seq_len, const int64_t *pos, size_t n,
+                           uint8_t *out, size_t *bad_index);
+
 /* ---- K1: pileup text -> consensus cells.  Replaces pileup.Reader.__iter__ + Record + ConsensusCaller +
  *      the loop body of call_consensus.py:161-188.
  *   mode SNPGPU_MODE_SITES   only lines whose (chrom,pos) is in the site table are parsed (pileup.py:423-429)

@@ -329,6 +329,28 @@ def fasta_text(seq_id: str, seq: str) -> str:
     return "".join(lines)
 
 
+def reference_snp_text(reference_fasta_path, snp_list_path):
+    """utils.write_reference_snp_file (utils.py:1091-1110) with Biopython's fasta reader / writer restated: one record
+    per reference contig in sorted id order, upper(seq[int(pos) - 1]) per snplist line of that contig."""
+    with open(snp_list_path) as f:
+        position_list = [line.split()[0:2] for line in f]
+    records, cur = {}, None
+    with open(reference_fasta_path) as f:
+        for line in f:
+            if line.startswith(">"):
+                cur = line[1:].split(None, 1)[0]
+                if cur in records:
+                    raise ValueError("Duplicate key '%s'" % cur)
+                records[cur] = []
+            elif cur is not None:
+                records[cur].append("".join(line.split()))
+    out = []
+    for rid in sorted(records):
+        seq = "".join(records[rid])
+        out.append(fasta_text(rid, "".join(seq[int(pos) - 1].upper() for chrom, pos in position_list if chrom == rid)))
+    return "".join(out)
+
+
 def read_fasta_matrix(path):
     """distance.py:76-84."""
     seqs = {}

@@ -24,7 +24,7 @@ EXPORTS = [
     "snpgpu_kernel_time", "snpgpu_sites_create", "snpgpu_sites_create_from_keys_dev",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
     "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end",
-    "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records",
+    "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_reference_bases",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
 ]
@@ -128,6 +128,8 @@ def load():
     L.snpgpu_pileup_consensus_dev.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, vp]
     L.snpgpu_normalize_newlines_dev.restype = ctypes.c_int
     L.snpgpu_normalize_newlines_dev.argtypes = [vp, vp, sz]
+    L.snpgpu_reference_bases.restype = ctypes.c_int
+    L.snpgpu_reference_bases.argtypes = [vp, vp, sz, vp, sz, vp, P(sz)]
     L.snpgpu_pileup_vcf_records.restype = ctypes.c_int
     L.snpgpu_pileup_vcf_records.argtypes = [vp, vp, P(Params), ctypes.c_int, vp, sz, P(sz), vp, sz, P(sz)]
     L.snpgpu_merge_sites.restype = ctypes.c_int
@@ -314,6 +316,20 @@ class Context(object):
         if lines is not None:
             return out_row, stats, lines[:stats.n_lines]
         return out_row, stats
+
+    def reference_bases(self, seq, pos):
+        """upper(seq[pos - 1]) for every 1-based position, with Python's indexing (snpgpu_reference_bases).
+        seq: uint8 array, pos: int64 array.  Raises IndexError where the reference's indexing does."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        out = np.zeros(pos.size, dtype=np.uint8)
+        bad = ctypes.c_size_t(0)
+        rc = self.lib.snpgpu_reference_bases(self.handle, _np_ptr(seq), seq.size, _np_ptr(pos), pos.size, _np_ptr(out),
+                                             ctypes.byref(bad))
+        if rc == E_INDEX:
+            raise IndexError("index out of range")             # what Bio.Seq / str indexing raises (utils.py:1108)
+        self._check(rc)
+        return out
 
     def pileup_vcf_records(self, sites, params, mode=MODE_SITES):
         """K5: the tallies behind the consensus VCF, one record per pileup line that the preceding pileup_consensus()

@@ -13,7 +13,7 @@ import argparse
 import sys
 
 from . import __version__
-from . import call_consensus, distance, merge_sites, snp_matrix, utils
+from . import call_consensus, distance, merge_sites, snp_matrix, snp_reference, utils
 
 
 def _min_cons_freq(value):
@@ -127,6 +127,22 @@ def parse_argument_list(argv):
                     help="Verbose message level (0=no info, 5=lots)")
     sp.add_argument("--version", **ver)
     sp.set_defaults(func=distance.calculate_snp_distances, excepthook=utils.handle_global_exception)
+
+    sp = subparsers.add_parser("snp_reference", help="Write reference bases at SNP locations to a fasta file",
+                               formatter_class=fc,
+                               description="Write reference sequence bases at SNP locations to a fasta file.")
+    sp.add_argument(dest="referenceFile", type=str,
+                    help="Relative or absolute path to the reference bases file in fasta format")
+    sp.add_argument("-f", "--force", dest="forceFlag", action="store_true",
+                    help="Force processing even when result file already exists and is newer than inputs")
+    sp.add_argument("-l", "--snpListFile", dest="snpListFile", type=str, default="snplist.txt", metavar="FILE",
+                    help="Relative or absolute path to the SNP list file")
+    sp.add_argument("-o", "--output", dest="snpRefFile", type=str, default="referenceSNP.fasta", metavar="FILE",
+                    help="Output file.  Relative or absolute path to the SNP reference sequence file")
+    sp.add_argument("-v", "--verbose", dest="verbose", type=int, default=1, metavar="0..5",
+                    help="Verbose message level (0=no info, 5=lots)")
+    sp.add_argument("--version", **ver)
+    sp.set_defaults(func=snp_reference.create_snp_reference_seq, excepthook=utils.handle_global_exception)
 
     return parser.parse_args(argv)
 

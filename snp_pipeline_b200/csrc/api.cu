@@ -379,6 +379,34 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
 
 size_t snpgpu_sites_n_snp(const snpgpu_sites *sites) { return sites ? sites->n_snp : 0; }
 
+// ------------------------------------------------------------------------------------------ reference bases (snp_reference)
+int snpgpu_reference_bases(snpgpu_ctx *ctx, const uint8_t *seq, size_t seq_len, const int64_t *pos, size_t n,
+                           uint8_t *out, size_t *bad_index) {
+    if (!ctx || (seq_len && !seq) || (n && (!pos || !out))) return fail(ctx, SNPGPU_E_ARG, "reference_bases: null argument");
+    if (bad_index) *bad_index = (size_t)-1;
+    if (!n) return SNPGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t o_pos = (seq_len + 255) & ~(size_t)255, o_out = o_pos + ((n * 8 + 255) & ~(size_t)255);
+    const size_t o_bad = o_out + ((n + 255) & ~(size_t)255);
+    CK(ctx->k3_tmp.ensure(o_bad + 256));
+    uint8_t *b = (uint8_t *)ctx->k3_tmp.p;
+    unsigned long long none = ~0ull, bad = ~0ull;
+    if (seq_len) CK(cudaMemcpyAsync(b, seq, seq_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_pos, pos, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_bad, &none, 8, cudaMemcpyHostToDevice, st));
+    ctx->launches += (uint64_t)k3_launch_reference_bases(st, b, seq_len, (const long long *)(b + o_pos), n, b + o_out,
+                                                         (unsigned long long *)(b + o_bad));
+    CK(cudaMemcpyAsync(out, b + o_out, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&bad, b + o_bad, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (bad != ~0ull) {
+        if (bad_index) *bad_index = (size_t)bad;
+        return fail(ctx, SNPGPU_E_INDEX, "reference_bases: position outside the sequence (the reference raises IndexError)");
+    }
+    return SNPGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------ K1
 static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
                   const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,

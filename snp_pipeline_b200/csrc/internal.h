@@ -27,6 +27,9 @@ int    k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, 
                  const int64_t *max_pos, uint32_t *bits, uint32_t *rank, size_t n_words, uint8_t *flags,
                  int32_t *snp_unique, SiteWord *words, void *tmp, size_t tmp_bytes);
 
+int    k3_launch_reference_bases(cudaStream_t stream, const uint8_t *seq, size_t seq_len, const long long *pos, size_t n,
+                                 uint8_t *out, unsigned long long *first_bad);
+
 // k2_merge.cu
 // sorted-unique union of keys with per-key sample lists; all pointers device; tmp: workspace owned by the caller
 size_t k2_workspace_bytes(size_t n);

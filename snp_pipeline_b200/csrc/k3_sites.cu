@@ -67,4 +67,25 @@ int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int
     return launches + 3;
 }
 
+// ---- reference bases at the snplist positions (utils.write_reference_snp_file, utils.py:1091-1110): out[k] =
+//      upper(seq[pos[k] - 1]) with Python's indexing -- position 0 and negative positions count from the end -- and the
+//      first position outside the sequence reported the way the reference's IndexError would surface --------------
+__global__ void k3_reference_bases_kernel(const uint8_t *seq, long long seq_len, const long long *pos, size_t n,
+                                          uint8_t *out, unsigned long long *first_bad) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    long long i = pos[k] - 1;
+    if (i < 0) i += seq_len;
+    if (i < 0 || i >= seq_len) { atomicMin(first_bad, (unsigned long long)k); out[k] = '?'; return; }
+    const unsigned c = seq[i];
+    out[k] = (uint8_t)((c - 'a' < 26u) ? c - 32u : c);
+}
+
+int k3_launch_reference_bases(cudaStream_t stream, const uint8_t *seq, size_t seq_len, const long long *pos, size_t n,
+                              uint8_t *out, unsigned long long *first_bad) {
+    if (!n) return 0;
+    k3_reference_bases_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seq, (long long)seq_len, pos, n, out, first_bad);
+    return 1;
+}
+
 }  // namespace snpgpu

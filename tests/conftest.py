@@ -36,9 +36,10 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden_dir(tmp_path_factory):
-    """Extract lambda / agona / listeria golden archives once per session; returns the directory."""
+    """Extract lambda / agona / listeria golden archives (and references/<dataset>.fasta) once per session; returns the
+    directory."""
     out = tmp_path_factory.mktemp("golden")
-    for name in ("lambda", "agona", "listeria"):
+    for name in ("lambda", "agona", "listeria", "references"):
         with tarfile.open(os.path.join(GOLDEN, name + ".tar.xz")) as tar:
             tar.extractall(out, filter="data")
     return str(out)

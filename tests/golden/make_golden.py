@@ -9,6 +9,7 @@ Produces
   ref_files.json.xz      whole-file known answers: small synthetic pileups pushed through the reference's
                          `cfsan_snp_pipeline call_consensus` (filter mode, --vcfAllPos mode, with -e exclude
                          files, multi-contig, duplicate positions, CRLF) -> consensus.fasta text or exit code
+  references.tar.xz      the three datasets' reference genomes (snp_reference's input)
   doctest_strip.json     the strip doctests of pileup.py:294-309 evaluated by the reference itself
 
 Usage:  python tests/golden/make_golden.py      (needs /root/reference; writes next to this script)
@@ -77,6 +78,21 @@ def make_datasets():
     pack("lambda", os.path.join(DATA, "lambdaVirusExpectedResults"), keep)
     pack("agona", os.path.join(DATA, "agonaExpectedResults"), keep)
     pack("listeria", os.path.join(DATA, "listeriaExpectedResults"), keep)
+
+
+def make_references():
+    """The reference genomes of the three bundled datasets (inputs of snp_reference), one archive."""
+    path = os.path.join(HERE, "references.tar.xz")
+    picks = [("lambda", "lambdaVirusInputs/reference/lambda_virus.fasta"), ("agona", "agonaInputs/reference/NC_011149.fasta"),
+             ("listeria", "listeriaInputs/reference/CFSAN023463.HGAP.draft.fasta")]
+    with tarfile.open(path, "w:xz", preset=9) as tar:
+        for name, rel in picks:
+            full = os.path.join(DATA, rel)
+            ti = tar.gettarinfo(full, arcname=os.path.join("references", name + ".fasta"))
+            ti.mtime, ti.uid, ti.gid, ti.uname, ti.gname, ti.mode = 0, 0, 0, "", "", 0o644
+            with open(full, "rb") as fh:
+                tar.addfile(ti, fh)
+    print("wrote", path, os.path.getsize(path))
 
 
 def make_ref_lines():
@@ -219,6 +235,7 @@ if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference tree not mounted at %s" % rh.REFERENCE_ROOT)
     make_datasets()
+    make_references()
     make_doctest_strip()
     make_ref_lines()
     make_ref_files()

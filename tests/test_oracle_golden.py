@@ -201,3 +201,14 @@ def test_fasta_writer_edges():
     assert orc.fasta_text("s", "") == ">s\n"                      # regression_tests.sh:5920-5934
     assert orc.fasta_text("s", "A" * 60) == ">s\n" + "A" * 60 + "\n"
     assert orc.fasta_text("s", "A" * 61) == ">s\n" + "A" * 60 + "\nA\n"
+
+
+@pytest.mark.parametrize("dataset", ["lambda", "agona", "listeria"])
+@pytest.mark.parametrize("suffix", ["", "_preserved"])
+def test_reference_snp_golden(golden_dir, dataset, suffix):
+    """snp_reference (scope row f2): the oracle's restatement of utils.write_reference_snp_file against the bundled
+    referenceSNP*.fasta of all three datasets."""
+    root = os.path.join(golden_dir, dataset)
+    ref = os.path.join(golden_dir, "references", dataset + ".fasta")
+    got = orc.reference_snp_text(ref, os.path.join(root, "snplist%s.txt" % suffix))
+    assert got == open(os.path.join(root, "referenceSNP%s.fasta" % suffix)).read()

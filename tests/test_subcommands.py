@@ -260,3 +260,47 @@ def test_distance_ragged_and_lowercase(tmp_path):
     (tmp_path / "bad.fasta").write_text(">a\nACGTACGT\n>b\nACG\n")
     with pytest.raises(IndexError):                                # a later sequence is shorter: the reference raises
         run("distance -v 0 -m %s/mx2.tsv %s/bad.fasta" % (tmp_path, tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dataset", ["lambda", "agona", "listeria"])
+@pytest.mark.parametrize("suffix", ["", "_preserved"])
+def test_snp_reference_golden(tmp_path, golden_dir, dataset, suffix, monkeypatch):
+    """`snp_reference` reproduces the bundled referenceSNP*.fasta byte for byte; freshness rule as in the reference."""
+    monkeypatch.setenv("errorOutputFile", str(tmp_path / "error.log"))
+    root = os.path.join(golden_dir, dataset)
+    ref = os.path.join(golden_dir, "references", dataset + ".fasta")
+    out = tmp_path / "referenceSNP.fasta"
+    line = "snp_reference -v 0 -l %s/snplist%s.txt -o %s %s" % (root, suffix, out, ref)
+    cli.run_command_from_args(cli.parse_command_line(line))
+    assert out.read_text() == open(os.path.join(root, "referenceSNP%s.fasta" % suffix)).read()
+    out.write_text("stale but newer than its inputs\n")
+    cli.run_command_from_args(cli.parse_command_line(line))
+    assert out.read_text() == "stale but newer than its inputs\n"          # not rebuilt without -f
+    cli.run_command_from_args(cli.parse_command_line(line.replace("snp_reference", "snp_reference -f", 1)))
+    assert out.read_text() == open(os.path.join(root, "referenceSNP%s.fasta" % suffix)).read()
+
+
+@pytest.mark.gpu
+def test_snp_reference_indexing_and_errors(tmp_path, monkeypatch):
+    """Python's indexing in utils.py:1108 (position 0 and negatives count from the end, anything further raises
+    IndexError -> exit 100 through handle_global_exception), several contigs, lower case, a contig without SNPs."""
+    from oracle import oracle as orc
+    from snp_pipeline_b200 import snp_reference
+    monkeypatch.setenv("errorOutputFile", str(tmp_path / "error.log"))
+    ref = tmp_path / "ref.fasta"
+    ref.write_text("; comment in front of the first record\n>b second contig\nacgtnACGTN\nrykm\n>a\nTTGCA\n  gg cc\n>empty\n")
+    snps = tmp_path / "snplist.txt"
+    snps.write_text("b\t1\t1\ts1\nb\t14\t1\ts1\na\t9\t2\ts1\ts2\nb\t0\t1\ts2\nb\t-3\t1\ts2\nzz\t5\t1\ts1\na\t1\t1\ts1\n")
+    want = orc.reference_snp_text(str(ref), str(snps))
+    assert want == ">a\nCT\n>b\nAMMR\n>empty\n"
+    assert snp_reference.reference_snp_text(str(ref), str(snps)) == want
+    snps.write_text("a\t10\t1\ts1\n")
+    with pytest.raises(IndexError):
+        snp_reference.reference_snp_text(str(ref), str(snps))
+    args = cli.parse_command_line("snp_reference -v 0 -l %s -o %s %s" % (snps, tmp_path / "o.fasta", ref))
+    with pytest.raises(IndexError):                                # uncaught, like in the reference ...
+        cli.run_command_from_args(args)
+    with pytest.raises(SystemExit) as e:                           # ... where the step's excepthook turns it into exit 100
+        args.excepthook(IndexError, IndexError("index out of range"), None)
+    assert e.value.code == 100
