@@ -673,6 +673,43 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         const bool file_start = tile == 0 && lane == 0 && wlen > 0;
         if (file_start) cnt++;                                // the first line of the file
+        if (!ALL) {
+            // ---- filter mode: no per-line output, so no file order is needed and a line is nearly always done after
+            //      its key columns -- every lane walks its own list of starts, no prefix sum, no list copy, no sort ----
+            const uint32_t n_mine = cnt;                      // (lane 0 of tile 0: the file's first line comes first)
+            const uint32_t n_steps = __reduce_max_sync(0xffffffffu, n_mine);
+            n_lines += __reduce_add_sync(0xffffffffu, n_mine);
+            K1Pass ps;
+            ps.base = base; ps.slot0 = ~0ull - 0xffffull; ps.wlen = wlen; ps.done = 0; ps.buffered = false; ps.eof = eof;
+            if (n_steps) {                                    // the next ticket, its latency hidden behind the parse
+                if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);
+                ticket_taken = true;
+            }
+            const uint32_t shift = file_start ? 1u : 0u;
+            for (uint32_t k = 0; k < n_steps; k++) {
+                const bool have = k < n_mine;
+                uint32_t code = 0, next = 0xffffu;
+                if (have) code = (file_start && k == 0u) ? 0xffffu : myhits[k - shift];
+                if (k + 1u < n_mine) next = myhits[k + 1u - shift];
+                uint32_t s = 0;
+                bool to_detail;
+                if (!HAS_QUAL) {
+                    to_detail = k1_quick_step<false>(a, sm, cc, ps, have, 0u, code, s, n_parsed);
+                } else {
+                    if (have && code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
+                    to_detail = have;
+                }
+                uint32_t len_hint = 0;                        // up to the '\n' in front of this lane's next start
+                if (to_detail && next != 0xffffu) len_hint = (next >> 5) * 16u + (next & 7u) * 4u + ((next >> 3) & 3u) - s;
+                n_dq = k1_push(sm.dq, n_dq, lane, to_detail, k1_entry(0u, len_hint, base + s));
+                if (n_dq >= 32u) {                            // leaves both queues below 32
+                    drained = true;
+                    const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
+                    n_dq = r & 0xffffu; n_gq = r >> 16;
+                }
+            }
+            continue;
+        }
         // ---- order: one prefix sum over the lanes ---------------------------------------------------
         uint32_t incl = cnt;
 #pragma unroll
