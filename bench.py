@@ -429,6 +429,28 @@ def main():
                 "k4": {"avg_launch_ms": k4_ms / max(k4_n, 1), "pair_sites_per_s":
                        (w.n * (world * w.n) * n_sites) / (k4_ms / max(k4_n, 1) * 1e-3) if k4_ms else None}}
 
+    # ---- the same kernel in the pipeline's default mode (only lines at snplist positions are parsed, no per-line
+    #      output: call_consensus without --vcfAllPos, run.py:709), reported next to the all-positions roofline ----------
+    sites_d = _lib.Sites.from_keys_dev(ctx, [CONTIG], [args.genome_len], w.uniq_dev.data_ptr(), n_sites) if world == 1 else None
+    if sites_d is not None:
+        row_d = torch.empty(max(n_sites, 1), dtype=torch.uint8, device="cuda")
+        for timed in (False, True):
+            ctx.enable_timing(timed)
+            ctx.kernel_time(0)
+            for i in range(w.n):
+                ctx.pileup_consensus_dev(w.texts[i].data_ptr(), w.nbytes[i], sites_d, w.params, w.lib.MODE_SITES,
+                                         row_d.data_ptr(), 0, 0, w.stats_dev[i].data_ptr())
+            torch.cuda.synchronize()
+        d_ms, d_n = ctx.kernel_time(0)
+        ctx.enable_timing(False)
+        sites_d.close()
+        d_bytes = (w.total_text + w.n * n_sites) / w.n
+        d_ach = d_bytes / (d_ms / max(d_n, 1) * 1e-3) / 1e9
+        roofline["default_mode"] = {"what": "k1_pileup_kernel with only the lines at snplist positions parsed (no --vcfAllPos)",
+                                    "avg_launch_ms": d_ms / max(d_n, 1), "alg_bytes_per_launch": d_bytes, "achieved": d_ach,
+                                    "frac": d_ach / peak, "launches_timed": d_n}
+        assert np.array_equal(w.stats_dev.cpu().numpy()[:, 0], stats[:, 0]), "default mode saw another number of lines"
+
     # ---- end to end through the host-buffer C ABI ---------------------------------------------------
     e2e = None
     if not args.no_e2e:

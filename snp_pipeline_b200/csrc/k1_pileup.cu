@@ -175,7 +175,7 @@ __device__ __forceinline__ unsigned long long k1_tile_peek(const PileupArgs &a, 
     return t >= 0 ? st[t] : (2ull << 62);
 }
 
-__device__ __forceinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane,
+__device__ __noinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane,
                                                               unsigned long long early = 0ull) {
     volatile unsigned long long *st = a.tile_state;
     const unsigned long long UPTO = 2ull << 62, VAL = (1ull << 62) - 1ull;
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         if (wlen > (uint32_t)K1_TILE) {                       // a whole tile: no chunk needs a bounds test
             uint32_t multi = 0;
             constexpr int B = 7;                              // chunks loaded together, ahead of the stores below
-#pragma unroll
+#pragma unroll 1
             for (int j0 = 0; j0 < K1_LANE_CHUNKS; j0 += B) {
                 uint4 vv[B];
 #pragma unroll
