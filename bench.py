@@ -184,6 +184,20 @@ def device_step(w, dist, world):
     return n_uniq, matrix, d
 
 
+def w_last_sites(w, ctx, dist, world, torch):
+    """The global sorted-unique site keys as this rank sees them (the exchange of device_step, repeated)."""
+    from snp_pipeline_b200 import sharding
+    n_uniq = ctx.merge_sites_dev(w.keys_dev.data_ptr(), w.samp_dev.data_ptr(), w.keys_host.size, w.uniq_dev.data_ptr(),
+                                 w.cnt_dev.data_ptr(), w.sout_dev.data_ptr())
+    parts = sharding.allgather_varlen(w.uniq_dev[:n_uniq], dist, world)
+    allkeys = torch.cat(parts)
+    owner = torch.cat([torch.full((int(p.numel()),), r, dtype=torch.int32, device="cuda") for r, p in enumerate(parts)])
+    gu = torch.empty_like(allkeys); gc = torch.empty(allkeys.numel(), dtype=torch.int32, device="cuda")
+    gs = torch.empty(allkeys.numel(), dtype=torch.int32, device="cuda")
+    n = ctx.merge_sites_dev(allkeys.data_ptr(), owner.data_ptr(), allkeys.numel(), gu.data_ptr(), gc.data_ptr(), gs.data_ptr())
+    return gu[:n].clone()
+
+
 def host_step(w, pool, pool_n, bufs, dist=None, world=1):
     """One end-to-end pass through the host-buffer C-ABI calls (what a ctypes user of the library makes).  With more
     than one rank the two exchange steps of device_step() happen here too, from and to host memory."""
@@ -406,6 +420,19 @@ def main():
     matrix_host = matrix[:, :n_sites].cpu().numpy()
     d_host = d.cpu().numpy()
 
+    # ---- multi-GPU: size-independent checks of the two exchange steps (outside the timed region) -------
+    if world > 1:
+        keys_now = w_last_sites(w, ctx, dist, world, torch)
+        sig = torch.stack([keys_now.sum(), keys_now.numel() * torch.ones((), dtype=torch.int64, device="cuda"),
+                           (keys_now * torch.arange(1, keys_now.numel() + 1, device="cuda")).sum()])
+        sigs = torch.empty((world, 3), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(sigs, sig)
+        assert bool((sigs == sigs[0]).all()), "the ranks disagree about the merged site list"
+        full_d = torch.empty((world * w.n, world * w.n), dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(full_d, d.contiguous())            # the ranks' row stripes, in rank order
+        assert bool((full_d == full_d.T).all()) and not bool(torch.diagonal(full_d).any()), \
+            "the distance matrix assembled from the ranks' stripes is not symmetric with a zero diagonal"
+
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peaks = {}
     try:
@@ -431,7 +458,7 @@ def main():
 
     # ---- the same kernel in the pipeline's default mode (only lines at snplist positions are parsed, no per-line
     #      output: call_consensus without --vcfAllPos, run.py:709), reported next to the all-positions roofline ----------
-    sites_d = _lib.Sites.from_keys_dev(ctx, [CONTIG], [args.genome_len], w.uniq_dev.data_ptr(), n_sites) if world == 1 else None
+    sites_d = _lib.Sites.from_keys_dev(ctx, [CONTIG], [args.genome_len], w.uniq_dev.data_ptr(), n_sites) if world == 1 else None   # (N = 1 only)
     if sites_d is not None:
         row_d = torch.empty(max(n_sites, 1), dtype=torch.uint8, device="cuda")
         for timed in (False, True):
