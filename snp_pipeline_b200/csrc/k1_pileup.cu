@@ -43,8 +43,7 @@ namespace snpgpu {
 struct K1Warp {                                 // one warp's slice of shared memory
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
     uint16_t starts[K1_WCAP];                   // line starts of the current pass, file order: chunk << 5 | flag bit
-    uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane;
-                                                // afterwards the length sort's permutation and histogram
+    uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
     uint16_t res[K1_RES_CAP];                   // per-line results of the tile parsed last, until they can be stored in file order
     alignas(16) uint32_t cname[K1_NAMEW];       // name + tab of the contig the warp expects (ContigCache::name4) ...
     alignas(16) uint32_t cmask[K1_NAMEW];       // ... and which of its bytes count (ContigCache::mask4)
@@ -74,7 +73,6 @@ __device__ __forceinline__ void pair_sync(int pipe) {          // (immediate bar
 }
 
 static_assert(K1_PAD >= (int)QUICK_PAD && K1_NAMEW % 4 == 0, "line_quick.cuh preconditions");
-static_assert(K1_WCAP <= 256 && K1_WCAP + 64 <= 2 * 32 * K1_LHCAP, "permutation (one byte per line) + histogram fit in lanehits");
 static_assert(sizeof(K1Warp) * K1_WARPS * K1_CTAS_PER_SM + 1024 * K1_CTAS_PER_SM <= 228 * 1024, "shared memory per SM");
 size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
 
@@ -456,7 +454,6 @@ template <bool ALL>
 __device__ __noinline__ void k1_helper(const PileupArgs &a, K1Warp &sm, int lane, int pipe) {
     ContigCache cc;
     contig_cache_attach(a.sites, -1, sm.cname, sm.cmask, K1_NAMEW, &cc);
-    const uint8_t *perm = reinterpret_cast<const uint8_t *>(sm.lanehits);
     uint32_t n_parsed = 0;
     for (;;) {
         pair_sync(pipe);                                      // the leader has a pass ready (or is out of tiles)
@@ -471,7 +468,7 @@ __device__ __noinline__ void k1_helper(const PileupArgs &a, K1Warp &sm, int lane
         uint32_t declined = 0;
         for (uint32_t l0 = 32u; l0 < n_pass; l0 += 64u) {
             const bool have = l0 + (uint32_t)lane < n_pass;
-            const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
+            const uint32_t l = have ? l0 + (uint32_t)lane : 0u;
             const uint32_t code = have ? sm.starts[l] : 0u;
             uint32_t s;
             const bool to_detail = k1_quick_step<ALL>(a, sm, cc, ps, have, l, code, s, n_parsed);
@@ -751,42 +748,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 __syncwarp();
             }
             const uint32_t n_pass = n_tile_lines - done < (uint32_t)K1_WCAP ? n_tile_lines - done : (uint32_t)K1_WCAP;
-            // ---- order the pass by line length (counting sort, 16 classes of 8 bytes): the 32 lines a warp
-            //      parses in lock step then run their loops about equally long.  perm/hist reuse lanehits. ----
-            uint8_t *perm = reinterpret_cast<uint8_t *>(sm.lanehits);
-            uint32_t *hist = reinterpret_cast<uint32_t *>(sm.lanehits) + 64;
-            if (lane < 16) hist[lane] = 0u;
-            __syncwarp();
-            uint32_t keys = 0;                                // 4 bits per line of this lane
-            unsigned long long ranks = 0;                     // 8 bits per line
-            for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u) {
-                const uint32_t c0 = sm.starts[l], c1 = l + 1u < n_pass ? sm.starts[l + 1u] : 0xffffu;
-                uint32_t key = 15u;
-                if (c0 != 0xffffu && c1 != 0xffffu) {         // bytes between consecutive starts
-                    const uint32_t len = ((c1 >> 5) - (c0 >> 5)) * 16u + ((c1 & 7u) - (c0 & 7u)) * 4u + (((c1 >> 3) & 3u) - ((c0 >> 3) & 3u));
-                    key = len < 32u ? 0u : (len - 32u) >> 3;
-                    key = key > 15u ? 15u : key;
-                }
-                const uint32_t r = atomicAdd(&hist[key], 1u);
-                keys |= key << (4u * k);
-                ranks |= (unsigned long long)r << (8u * k);
-            }
-            __syncwarp();
-            {
-                const uint32_t v = lane < 16 ? hist[lane] : 0u;
-                uint32_t inc = v;
-#pragma unroll
-                for (int d = 1; d < 16; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                __syncwarp();
-                if (lane < 16) hist[lane] = inc - v;
-            }
-            __syncwarp();
-            for (uint32_t k = 0, l = (uint32_t)lane; l < n_pass; k++, l += 32u)
-                perm[hist[(keys >> (4u * k)) & 15u] + (uint32_t)((ranks >> (8u * k)) & 0xffu)] = (uint8_t)l;
-            __syncwarp();
+            // (The lines are parsed in file order.  Sorting a pass by line length, so that the 32 lines of a step run
+            //  their loops equally long, was measured: the counting sort costs more than the divergence it removes.)
             // ---- the pass's lines, 32 per step; with a helper warp the leader takes the even steps ----------
             const bool use_helper = K1_HELPER && !HAS_QUAL && n_pass > 32u;
             K1Pass ps;
@@ -825,7 +788,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             }
             for (uint32_t l0 = 0; l0 < n_pass; l0 += use_helper ? 64u : 32u) {
                 const bool have = l0 + (uint32_t)lane < n_pass;
-                const uint32_t l = have ? perm[l0 + (uint32_t)lane] : 0u;
+                const uint32_t l = have ? l0 + (uint32_t)lane : 0u;
                 const uint32_t code = have ? sm.starts[l] : 0u;
                 uint32_t s = 0;
                 bool to_detail;
