@@ -39,7 +39,7 @@ struct snpgpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t     launches = 0;
     std::string  err;
-    DevBuf k1_zero, tile_first, arena, stats;   // k1_zero: status | tile_state | site_cells, cleared by one memset per call
+    DevBuf k1_zero, tile_first, tile_lines, stage, over, arena, stats;   // k1_zero: status | site_cells, cleared by one memset per call
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     size_t text_nbytes = 0;                   // bytes of the last text snpgpu_pileup_consensus() staged ...
     bool   text_valid = false;                // ... still there (snpgpu_pileup_vcf_records works on it)
@@ -62,6 +62,7 @@ struct snpgpu_ctx {
     cudaEvent_t lane_event = nullptr;
     std::vector<std::pair<void *, size_t>> sites_pool;   // blobs of destroyed device-built site tables, reused in stream order
     size_t arena_want = 1 << 20;
+    size_t over_want = 1 << 16;              // entries of the per-line results' overflow list (tiles of tiny lines)
     bool   timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];     // pending event pairs per kernel id
     std::vector<cudaEvent_t> spare_events;
@@ -145,7 +146,7 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
         if (ctx->lane_stats[k]) cudaFreeHost(ctx->lane_stats[k]);
     }
     if (ctx->lane_event) cudaEventDestroy(ctx->lane_event);
-    DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->arena,
+    DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->tile_lines, &ctx->stage, &ctx->over, &ctx->arena,
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
                      &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
@@ -421,14 +422,18 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
     cudaStream_t st = ctx->stream;
     const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out_dev != nullptr;
-    // per-call scratch that starts as zeros, in one allocation: status | tile_state | site_cells
-    const size_t z_status = 0, z_tiles = 256;
-    const size_t z_cells = z_tiles + (want_lines ? (((size_t)n_tiles + 1) * sizeof(unsigned long long) + 255) & ~(size_t)255 : 0);
+    // per-call scratch that starts as zeros, in one allocation: status | site_cells
+    const size_t z_status = 0, z_cells = 256;
     const size_t z_total = z_cells + (sites->n_unique + 1) * sizeof(unsigned long long);
-    static_assert(sizeof(PileupStatusDev) <= 256, "status block");
+    static_assert(sizeof(PileupStatusDev) <= 64, "status block (the tuning build's counters follow it)");
     CK(ctx->k1_zero.ensure(z_total));
     CK(ctx->arena.ensure(ctx->arena_want));
-    if (want_lines) CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+    if (want_lines) {                                         // per-line results: staged per tile, ordered afterwards
+        CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+        CK(ctx->tile_lines.ensure(((size_t)n_tiles + 1) * sizeof(uint32_t)));
+        CK(ctx->stage.ensure(((size_t)n_tiles + 1) * K1_STAGE_CAP * sizeof(uint16_t)));
+        CK(ctx->over.ensure(ctx->over_want * sizeof(unsigned long long)));
+    }
     CK(cudaMemsetAsync(ctx->k1_zero.p, 0, z_total, st));
     uint8_t *zb = (uint8_t *)ctx->k1_zero.p;
     PileupArgs a;
@@ -441,7 +446,10 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
     a.site_cells = (unsigned long long *)(zb + z_cells);
     a.line_out = want_lines ? line_out_dev : nullptr;
     a.line_out_cap = want_lines ? (unsigned long long)line_out_cap : 0ull;
-    a.tile_state = want_lines ? (unsigned long long *)(zb + z_tiles) : nullptr;
+    a.tile_lines = want_lines ? (uint32_t *)ctx->tile_lines.p : nullptr;
+    a.stage = want_lines ? (uint16_t *)ctx->stage.p : nullptr;
+    a.over = want_lines ? (unsigned long long *)ctx->over.p : nullptr;
+    a.over_cap = want_lines ? (unsigned long long)ctx->over_want : 0ull;
     a.tile_first = want_lines ? (unsigned long long *)ctx->tile_first.p : nullptr;
     a.st = (PileupStatusDev *)(zb + z_status);
     a.rec_off = rec_off; a.rec_count = rec_count; a.rec_cap = rec_cap;
@@ -452,7 +460,9 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
         TimedLaunch t(ctx, SNPGPU_KERNEL_PILEUP);
         ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
     }
-    ctx->launches += (uint64_t)k1_launch_finish(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev, a.st, stats_dev);
+    ctx->launches += (uint64_t)k1_launch_order(st, a);
+    ctx->launches += (uint64_t)k1_launch_finish(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev, a.st, a.over_cap,
+                                                stats_dev);
     CK(cudaGetLastError());
     return SNPGPU_OK;
 }
@@ -495,8 +505,9 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
             skip_copy = true;
             continue;
         }
-        if (hs.error_code == SNPGPU_E_NOMEM && attempt == 0) {    // the exact-splice scratch was too small: grow, redo
-            ctx->arena_want = (size_t)hs.error_offset + (1 << 20);
+        if (hs.error_code == SNPGPU_E_NOMEM && attempt == 0) {    // the splice scratch or the overflow list was too small: grow, redo
+            if (hs.error_offset) ctx->arena_want = (size_t)hs.error_offset + (1 << 20);
+            if (hs.reserved > 0) ctx->over_want = ((size_t)hs.reserved << 10) + (1 << 16);
             continue;
         }
         if (want_lines && hs.error_code == 0) {

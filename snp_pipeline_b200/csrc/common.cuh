@@ -20,6 +20,7 @@ struct PileupStatusDev {
     unsigned long long arena_used;    // bytes of scratch claimed by the exact-splice path
     unsigned int       arena_overflow;
     unsigned int       next_tile;     // the pileup kernel's tile tickets (warps take tiles in increasing order)
+    unsigned long long over_used;     // entries claimed in the per-line results' overflow list
 };
 
 // Tile geometry of the pileup kernel: every warp is its own pipeline.
@@ -29,23 +30,18 @@ struct PileupStatusDev {
 #define K1_CFG_LHCAP 10
 #define K1_CFG_QCAP 64
 #endif
-#ifndef K1_CFG_HELPER
-#define K1_CFG_HELPER 0
-#endif
 constexpr int K1_LANE_CHUNKS = K1_CFG_CHUNKS;             // 16-byte chunks one lane scans for newlines ...
 constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
 constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
 constexpr int K1_LOOK     = 896;               // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_WARPS    = 4;                 // independent pipelines per CTA: a leader warp each ...
-constexpr int K1_HELPER   = K1_CFG_HELPER;     // ... plus (1) a helper warp that parses every other group of 32 lines.
-                                               // Off: at the 64 registers 32 warps per SM leave, the leader spills to L2 (measured -45 %)
-constexpr int K1_THREADS  = 32 * K1_WARPS * (1 + K1_HELPER);
+constexpr int K1_WARPS    = 4;                 // independent warps per CTA
+constexpr int K1_THREADS  = 32 * K1_WARPS;
 constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
 constexpr int K1_WCAP     = 192;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)
-constexpr int K1_RES_CAP  = 160;               // per-line results of a parsed tile kept in shared memory (K1Warp::res) until its first
-                                               // line's file-order index is known; tiles with more lines write theirs directly
+constexpr int K1_STAGE_CAP = 320;              // per-line results a tile keeps in its row of the staging array (a tile of the
+                                               // scan's own path owns at most 32 (K1_LHCAP - 1) + 1 lines; more -> overflow list)
 constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
 constexpr int K1_DRAIN_AT = 24;                // queued lines that trigger a drain between two tiles (32: also inside a tile)
 constexpr int K1_QCAP     = K1_CFG_QCAP;                // per-warp queue slots (drained whenever 32 are filled)
@@ -61,8 +57,11 @@ struct PileupArgs {
                                        // the last line in file order wins, like the dict of call_consensus.py:169)
     uint16_t           *line_out;      // null, or one uint16 per line in file order: cell | fail << 8
     unsigned long long  line_out_cap;
-    unsigned long long *tile_state;    // [n_tiles], zero-initialised: decoupled look-back over the tiles' line counts
-    unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (set by the warp that owns it)
+    uint32_t           *tile_lines;    // [n_tiles]: lines each tile owns (written by the tile's warp, when line_out)
+    uint16_t           *stage;         // [n_tiles][K1_STAGE_CAP]: per-line results, tile by tile (when line_out)
+    unsigned long long *over;          // overflow list of (tile << 32 | index << 16 | result) for tiles above K1_STAGE_CAP ...
+    unsigned long long  over_cap;      // ... its capacity (PileupStatusDev::over_used counts the claims)
+    unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (k1_tile_prefix_kernel)
     unsigned long long *rec_off;       // null, or: file offset of every parsed line is appended here (any order) ...
     unsigned long long *rec_count;     // ... through this counter (the consensus-VCF pass, k5_vcf.cu)
     unsigned long long  rec_cap;

@@ -44,34 +44,12 @@ struct K1Warp {                                 // one warp's slice of shared me
     alignas(128) uint8_t buf[K1_TILE + K1_LOOK + K1_PAD];
     uint16_t starts[K1_WCAP];                   // line starts of the current pass, file order: chunk << 5 | flag bit
     uint16_t lanehits[32 * K1_LHCAP];           // the same as each lane found them during the scan, K1_LHCAP per lane
-    uint16_t res[K1_RES_CAP];                   // per-line results of the tile parsed last, until they can be stored in file order
     alignas(16) uint32_t cname[K1_NAMEW];       // name + tab of the contig the warp expects (ContigCache::name4) ...
     alignas(16) uint32_t cmask[K1_NAMEW];       // ... and which of its bytes count (ContigCache::mask4)
     unsigned long long dq[K1_QCAP];             // lines for line_fast.cuh (k1_entry)
     unsigned long long gq[K1_QCAP];             // lines for line_general.cuh, same encoding
     alignas(8) uint64_t bar;
-    // what the leader hands its helper warp for one pass (K1_HELPER), and what the helper hands back
-    unsigned long long h_base, h_slot0;         // file offset of the window; file-order index of the tile's first line
-    uint32_t h_wlen, h_n_pass, h_done;
-    uint32_t h_flags;                           // H_BUFFERED | H_EOF | H_EXIT
-    int32_t  h_cid;                             // the contig the leader expects
-    uint32_t h_declined;                        // helper -> leader: H_DECLINED (lines marked in starts[]) | H_DECLINED_FIRST
 };
-enum : uint32_t { H_BUFFERED = 1, H_EOF = 2, H_EXIT = 4, H_DECLINED = 1, H_DECLINED_FIRST = 2 };
-enum : uint32_t { START_MARK = 0x8000u, START_CODE = 0x7fffu };   // starts[]: bit 15 = "declined by the helper, the leader's to queue"
-static_assert((32 * K1_LANE_CHUNKS) << 5 <= (int)START_MARK, "start codes leave bit 15 free");
-
-// the two warps of a pipeline meet here (named barrier 1 + pipeline, 64 threads)
-__device__ __forceinline__ void pair_sync(int pipe) {          // (immediate barrier numbers: only 1 + K1_WARPS get reserved)
-    static_assert(K1_WARPS == 4, "one case per pipeline");
-    switch (pipe) {
-        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
-}
-
 static_assert(K1_PAD >= (int)QUICK_PAD && K1_NAMEW % 4 == 0, "line_quick.cuh preconditions");
 static_assert(sizeof(K1Warp) * K1_WARPS * K1_CTAS_PER_SM + 1024 * K1_CTAS_PER_SM <= 228 * 1024, "shared memory per SM");
 size_t k1_smem_bytes() { return sizeof(K1Warp) * K1_WARPS; }
@@ -138,67 +116,25 @@ __device__ __forceinline__ uint16_t k1_cell_flags(const PileupArgs &a, unsigned 
     return (uint16_t)(cell | (fail << 8));
 }
 
-// the same, stored at the line's file-order index `slot` of line_out (~0 for none)
-__device__ __forceinline__ void k1_emit(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
-                                        unsigned long long goff, unsigned long long slot) {
-    const uint16_t v = k1_cell(a, base_ch, fail, site, goff);
-    if (slot < a.line_out_cap) a.line_out[slot] = v;
-}
-
-// file-order index of the line that starts at file offset goff and is the line_idx-th of its tile (the tile
-// holding the byte in front of it).  Only the warp that owns the tile asks, after it has set tile_first.
-__device__ __forceinline__ unsigned long long k1_line_slot(const PileupArgs &a, unsigned long long goff, uint32_t line_idx) {
-    if (!a.line_out) return ~0ull;
-    const unsigned long long tile = goff ? (goff - 1ull) / (unsigned long long)K1_TILE : 0ull;
-    return a.tile_first[tile] + line_idx;
-}
-
-// Decoupled look-back over the tiles' line counts.  One 64-bit word per tile carries a 2-bit state (0 nothing
-// yet, 1 the tile's own count, 2 the count of all tiles up to and including it) and the value.
-// k1_tile_publish: tile `tile` owns n lines (right after its scan).  k1_tile_resolve (all 32 lanes): how many lines
-// the earlier tiles own, i.e. the file-order index of this tile's first line; also recorded in tile_first.
-// Tiles are handed out by ticket (PileupStatusDev::next_tile), so every tile in front of a warp's own was taken
-// earlier by a resident warp, which publishes its count right after its scan and before it waits for anybody:
-// the wait always ends.  The kernel resolves a tile only after parsing it, when the tiles in front have long
-// published and most have resolved, so the look-back is usually one round of 32.
-__device__ __forceinline__ void k1_tile_publish(const PileupArgs &a, int tile, uint32_t n) {
-    volatile unsigned long long *st = a.tile_state;
-    st[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (unsigned long long)n;
-}
-
-// the look-back's first window for `tile`, asked for ahead of time (k1_tile_resolve's `early`): lane L's view of tile - 1 - L
-__device__ __forceinline__ unsigned long long k1_tile_peek(const PileupArgs &a, int tile, int lane) {
-    volatile unsigned long long *st = a.tile_state;
-    const int t = tile - 1 - lane;
-    return t >= 0 ? st[t] : (2ull << 62);
-}
-
-__device__ __noinline__ unsigned long long k1_tile_resolve(const PileupArgs &a, int tile, uint32_t n, int lane,
-                                                              unsigned long long early = 0ull) {
-    volatile unsigned long long *st = a.tile_state;
-    const unsigned long long UPTO = 2ull << 62, VAL = (1ull << 62) - 1ull;
-    unsigned long long before = 0;
-    if (tile > 0) {
-        for (int j = tile - 1;; j -= 32) {                    // lane L looks at tile j - L
-            const int t = j - lane;
-            unsigned long long v = UPTO;                      // in front of tile 0: nothing
-            if (t >= 0) {
-                v = j == tile - 1 && (early >> 62) != 0ull ? early : st[t];      // (an early view is as good as a late one)
-                while ((v >> 62) == 0ull) { __nanosleep(100); v = st[t]; }
-            }
-            const uint32_t upto = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-            const int stop = upto ? __ffs((int)upto) - 1 : 32;    // nearest tile that knows its running total
-            before += (unsigned long long)__reduce_add_sync(0xffffffffu, lane < stop ? (uint32_t)v : 0u);   // own counts < 2^32
-            if (upto) {
-                before += __shfl_sync(0xffffffffu, v & VAL, stop);
-                break;
-            }
-        }
-        if (lane == 0) st[tile] = UPTO | (before + (unsigned long long)n);
+// Per-line results (all-positions mode with line_out): a line's result goes to slot `line_idx` of its tile's row of
+// the staging array; the tiles' line counts (PileupArgs::tile_lines) and the rows are put into file order afterwards
+// by k1_tile_prefix_kernel + k1_lines_kernel.  No tile has to know where it starts while the pileup kernel runs.
+// A tile that owns more than K1_STAGE_CAP lines (only the byte-wise path can: lines of a few bytes) appends the rest
+// to an overflow list of (tile, index, result) entries.
+__device__ __forceinline__ void k1_store_line(const PileupArgs &a, unsigned long long tile, uint32_t line_idx, uint16_t v) {
+    if (line_idx < (uint32_t)K1_STAGE_CAP) {
+        a.stage[tile * (unsigned long long)K1_STAGE_CAP + line_idx] = v;
+    } else {
+        const unsigned long long k = atomicAdd(&a.st->over_used, 1ull);
+        if (k < a.over_cap) a.over[k] = (tile << 32) | ((unsigned long long)line_idx << 16) | (unsigned long long)v;
     }
-    if (lane == 0) a.tile_first[tile] = before;
-    __syncwarp();
-    return before;
+}
+
+// the line that starts at file offset goff and is the line_idx-th of its tile (the tile holding the byte in front of it)
+__device__ __forceinline__ void k1_emit(const PileupArgs &a, unsigned base_ch, unsigned fail, int32_t site,
+                                        unsigned long long goff, uint32_t line_idx) {
+    const uint16_t v = k1_cell(a, base_ch, fail, site, goff);
+    if (a.line_out) k1_store_line(a, goff ? (goff - 1ull) / (unsigned long long)K1_TILE : 0ull, line_idx, v);
 }
 
 // third tier: the exact any-input parser, on the text where it lies in global memory
@@ -235,7 +171,7 @@ __device__ __noinline__ void k1_general(const PileupArgs &a, K1Cold &cs, unsigne
         int cid = contig_find(a.sites, line + r.chrom_off, r.chrom_len);
         site = site_find(a.sites, cid, r.pos);
     }
-    k1_emit(a, r.base, r.fail, site, goff, k1_line_slot(a, goff, line_idx));
+    k1_emit(a, r.base, r.fail, site, goff, line_idx);
     cs.n_parsed++;
 }
 
@@ -269,7 +205,7 @@ __device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned
     FastLine fl;
     const int st = fast_line<HAS_QUAL>(buf, s, s + n, a.sites, cs.hint, a.p, ALL, &fl);
     if (st == ST_OK) {
-        k1_emit(a, fl.base, fl.fail, fl.site, goff, k1_line_slot(a, goff, line_idx));
+        k1_emit(a, fl.base, fl.fail, fl.site, goff, line_idx);
         cs.n_parsed++;
     }
     return st == ST_FALLBACK;
@@ -349,10 +285,7 @@ __device__ __noinline__ uint32_t k1_slow_tile(const PileupArgs &a, K1Warp &sm, K
         if (lane >= d) incl += o;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (a.line_out) {
-        if (lane == 0) k1_tile_publish(a, tile, total);
-        k1_tile_resolve(a, tile, total, lane);
-    }
+    if (a.line_out && lane == 0) a.tile_lines[tile] = total;
     uint32_t idx = incl - cnt, cur = lo;
     bool pending_first = first;
     while (__any_sync(0xffffffffu, cnt > 0u)) {
@@ -417,16 +350,16 @@ __device__ __noinline__ void k1_relist(K1Warp &sm, int lane, uint32_t wlen, uint
 }
 
 // One first-tier step of a pass: the lane's line l of the pass (have: it has one).  Returns true when the line has
-// to go on to the second tier; s = offset of the line in the window.  Shared by the leader and its helper warp.
+// to go on to the second tier; s = offset of the line in the window.
 struct K1Pass {
-    unsigned long long base, slot0;
+    unsigned long long base;                    // file offset of the window
+    unsigned long long tile;
     uint32_t wlen, done;
-    bool buffered, eof;
+    bool eof;
 };
 template <bool ALL>
 __device__ __forceinline__ bool k1_quick_step(const PileupArgs &a, K1Warp &sm, const ContigCache &cc, const K1Pass &ps,
                                               bool have, uint32_t l, uint32_t code, uint32_t &s, uint32_t &n_parsed) {
-    uint16_t *res = sm.res;
     const uint32_t line_idx = ps.done + l;
     s = 0;                                                    // code: chunk << 5 | flag bit 8*b + w  ->  byte 4*w + b of the chunk
     if (have && code != 0xffffu) s = (code >> 5) * 16u + (code & 7u) * 4u + ((code >> 3) & 3u) + 1u;
@@ -438,53 +371,12 @@ __device__ __forceinline__ bool k1_quick_step(const PileupArgs &a, K1Warp &sm, c
         if (st == ST_SKIP) to_detail = false;
         else if (st == ST_OK && !(q.end == ps.wlen && !ps.eof)) {     // (a line that leaves the window goes on)
             const uint16_t v = k1_cell_flags(a, q.base, q.fail, q.site, q.flags, ps.base + s);
-            if (ps.buffered) res[line_idx] = v;
-            else if (ps.slot0 + line_idx < a.line_out_cap) a.line_out[ps.slot0 + line_idx] = v;
+            if (ALL && a.line_out) k1_store_line(a, ps.tile, line_idx, v);
             n_parsed++;
             to_detail = false;
         }
     }
     return to_detail;
-}
-
-// The helper warp of a pipeline (K1_HELPER): between two meetings with its leader it runs the first tier over every
-// other group of 32 lines of the pass the leader has listed and sorted.  It owns no queue: a line the first tier
-// declines is marked in starts[] (bit 15) and queued by the leader afterwards.
-template <bool ALL>
-__device__ __noinline__ void k1_helper(const PileupArgs &a, K1Warp &sm, int lane, int pipe) {
-    ContigCache cc;
-    contig_cache_attach(a.sites, -1, sm.cname, sm.cmask, K1_NAMEW, &cc);
-    uint32_t n_parsed = 0;
-    for (;;) {
-        pair_sync(pipe);                                      // the leader has a pass ready (or is out of tiles)
-        const uint32_t flags = sm.h_flags;
-        if (flags & H_EXIT) break;
-        const int cid = sm.h_cid;
-        if (cid != cc.cid) contig_cache_attach(a.sites, cid, sm.cname, sm.cmask, K1_NAMEW, &cc);
-        K1Pass ps;
-        ps.base = sm.h_base; ps.slot0 = sm.h_slot0; ps.wlen = sm.h_wlen; ps.done = sm.h_done;
-        ps.buffered = (flags & H_BUFFERED) != 0u; ps.eof = (flags & H_EOF) != 0u;
-        const uint32_t n_pass = sm.h_n_pass;
-        uint32_t declined = 0;
-        for (uint32_t l0 = 32u; l0 < n_pass; l0 += 64u) {
-            const bool have = l0 + (uint32_t)lane < n_pass;
-            const uint32_t l = have ? l0 + (uint32_t)lane : 0u;
-            const uint32_t code = have ? sm.starts[l] : 0u;
-            uint32_t s;
-            const bool to_detail = k1_quick_step<ALL>(a, sm, cc, ps, have, l, code, s, n_parsed);
-            if (to_detail) {
-                if (code == 0xffffu) declined |= H_DECLINED_FIRST;        // (the file's first line has no code to mark)
-                else { sm.starts[l] = (uint16_t)(code | START_MARK); declined |= H_DECLINED; }
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) declined |= __shfl_xor_sync(0xffffffffu, declined, d);
-        if (lane == 0) sm.h_declined = declined;
-        pair_sync(pipe);                                      // done with the window and the lists
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n_parsed += __shfl_xor_sync(0xffffffffu, n_parsed, d);
-    if (lane == 0 && n_parsed) atomicAdd(&a.st->n_parsed, (unsigned long long)n_parsed);
 }
 
 // HAS_QUAL: a minimum base quality is set (call_consensus -q > 0): every line goes straight to line_fast.cuh,
@@ -494,21 +386,8 @@ template <bool HAS_QUAL, bool ALL>
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(const __grid_constant__ PileupArgs a) {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
     const int lane = threadIdx.x & 31;
-    // warps 0 .. K1_WARPS-1 lead the pipelines, warps K1_WARPS .. 2 K1_WARPS-1 help them (one warpgroup each, so that
-    // the register file can be re-split between the two roles)
-    const int warp = (int)(threadIdx.x >> 5) % K1_WARPS;      // the pipeline this warp belongs to
-    const bool helper = K1_HELPER && (int)(threadIdx.x >> 5) >= K1_WARPS;
+    const int warp = (int)(threadIdx.x >> 5);
     K1Warp &sm = reinterpret_cast<K1Warp *>(k1_smem_raw)[warp];
-    if (helper) {
-#if K1_HELPER && defined(K1_CFG_HELPER_REGS)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K1_CFG_HELPER_REGS));
-#endif
-        if (!HAS_QUAL) k1_helper<ALL>(a, sm, lane, warp);     // (with a minimum base quality the first tier is not used)
-        return;
-    }
-#if K1_HELPER && defined(K1_CFG_HELPER_REGS)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(128 - K1_CFG_HELPER_REGS));
-#endif
     if (lane == 0) {
         mbar_init(&sm.bar, 1);
         mbar_fence_init();
@@ -524,38 +403,11 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     ContigCache cc;
     contig_cache_load(a.sites, 0, sm.cname, sm.cmask, K1_NAMEW, &cc);   // every lane writes the same words
     __syncwarp();
-    // Per-line results of the tile just parsed wait in shared memory (the tail of lanehits) until the file-order
-    // index of the tile's first line is known -- resolved one tile later, while the next window is in flight.
-    uint16_t *res = sm.res;
-    int pend_tile = -1;                                       // tile whose results sit in res
-    uint32_t pend_n = 0;
-    bool pend_known = false;
-    unsigned long long pend_first = 0;
-    unsigned long long pend_early = 0;                        // this lane's early view of the look-back window (0: none)
-    auto resolve_pending = [&]() {                            // (needed before any queued line of that tile is emitted)
-        if (pend_tile >= 0 && !pend_known) {
-            pend_first = k1_tile_resolve(a, pend_tile, pend_n, lane, pend_early);
-            pend_known = true;
-        }
-        pend_early = 0;
-    };
-    auto flush_pending = [&]() {
-        if (pend_tile < 0) return;
-        resolve_pending();
-        __syncwarp();
-        for (uint32_t i = (uint32_t)lane; i < pend_n; i += 32u) {
-            const uint16_t v = res[i];                        // 0xffff: the line went to a queue and is emitted from there
-            if (v != 0xffffu && pend_first + i < a.line_out_cap) a.line_out[pend_first + i] = v;
-        }
-        __syncwarp();
-        pend_tile = -1;
-    };
-
     int ticket = 0;                                           // lane 0: the next tile, when ticket_taken
     bool drained = false;                                     // queued lines ran since the contig cache was last checked
     bool ticket_taken = false;                                // (warp-uniform)
     for (;;) {
-        // tiles in increasing order (see k1_tile_resolve); usually taken during the last parse step of the tile before
+        // tiles in increasing order; usually taken while the tile before is parsed
         if (!ticket_taken && lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);
         const int tile = __shfl_sync(0xffffffffu, ticket, 0);
         PROF(0);                                              // (waiting for the warp's slowest lane and the ticket)
@@ -593,12 +445,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
             sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
         PROF(1);
-        // the previous tile's results are stored after this window's scan; the look-back they need is asked for now, so
-        // that its trip to L2 hides behind the window's arrival and the scan
-        if (pend_tile >= 0 && !pend_known) pend_early = k1_tile_peek(a, pend_tile, lane);
         PROF(2);
-        if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines: every tile they belong to must be resolved first
-            flush_pending();
+        if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines, while this window loads
             drained = true;
             const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
             n_dq = r & 0xffffu; n_gq = r >> 16;
@@ -677,7 +525,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             const uint32_t n_steps = __reduce_max_sync(0xffffffffu, n_mine);
             n_lines += __reduce_add_sync(0xffffffffu, n_mine);
             K1Pass ps;
-            ps.base = base; ps.slot0 = ~0ull - 0xffffull; ps.wlen = wlen; ps.done = 0; ps.buffered = false; ps.eof = eof;
+            ps.base = base; ps.tile = (unsigned long long)tile; ps.wlen = wlen; ps.done = 0; ps.eof = eof;
             if (n_steps) {                                    // the next ticket, its latency hidden behind the parse
                 if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);
                 ticket_taken = true;
@@ -716,19 +564,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         }
         const uint32_t n_tile_lines = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t first_idx = incl - cnt;
-        // per-line results: published count now, index of the first line later (see flush_pending)
-        bool buffered = false;
-        unsigned long long slot0 = ~0ull - 0xffffull;
-        if (a.line_out) {
-            if (lane == 0) k1_tile_publish(a, tile, n_tile_lines);
-            flush_pending();                                  // the previous tile's results leave sm.res
-            if (n_tile_lines <= (uint32_t)K1_RES_CAP) {
-                buffered = true;
-                pend_tile = tile; pend_n = n_tile_lines; pend_known = false;
-            } else {
-                slot0 = k1_tile_resolve(a, tile, n_tile_lines, lane);
-            }
-        }
+        // per-line results go to the tile's row of the staging array; its line count is all the ordering pass needs
+        if (a.line_out && lane == 0) a.tile_lines[tile] = n_tile_lines;
         PROF(6);
         // ---- the warp's list, file order (the first K1_WCAP starts; more -> later passes scan again) -----
         {
@@ -750,43 +587,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             const uint32_t n_pass = n_tile_lines - done < (uint32_t)K1_WCAP ? n_tile_lines - done : (uint32_t)K1_WCAP;
             // (The lines are parsed in file order.  Sorting a pass by line length, so that the 32 lines of a step run
             //  their loops equally long, was measured: the counting sort costs more than the divergence it removes.)
-            // ---- the pass's lines, 32 per step; with a helper warp the leader takes the even steps ----------
-            const bool use_helper = K1_HELPER && !HAS_QUAL && n_pass > 32u;
+            // ---- the pass's lines, 32 per step, in file order ---------------------------------------------
             K1Pass ps;
-            ps.base = base; ps.slot0 = slot0; ps.wlen = wlen; ps.done = done; ps.buffered = buffered; ps.eof = eof;
-            if (use_helper) {
-                if (lane == 0) {
-                    sm.h_base = base; sm.h_slot0 = slot0; sm.h_wlen = wlen; sm.h_n_pass = n_pass; sm.h_done = done;
-                    sm.h_flags = (buffered ? H_BUFFERED : 0u) | (eof ? H_EOF : 0u);
-                    sm.h_cid = cc.cid;
-                }
-                pair_sync(warp);                              // lists, permutation and hand-over block are complete
-            }
+            ps.base = base; ps.tile = (unsigned long long)tile; ps.wlen = wlen; ps.done = done; ps.eof = eof;
             PROF(8);
-            // a line for the second tier: its result slot is marked, it is queued with its length (up to the '\n' in
-            // front of the next listed start), and the queue is run when 32 wait
-            auto queue_line = [&](bool to_detail, uint32_t l, uint32_t s) {
-                const uint32_t line_idx = done + l;
-                if (buffered && to_detail) res[line_idx] = 0xffffu;       // emitted from the queue, not by flush_pending
-                uint32_t len_hint = 0;
-                if (to_detail && l + 1u < n_pass) {
-                    const uint32_t c1 = sm.starts[l + 1u] & START_CODE;
-                    len_hint = (c1 >> 5) * 16u + (c1 & 7u) * 4u + ((c1 >> 3) & 3u) - s;
-                }
-                const unsigned long long entry = k1_entry(line_idx, len_hint, base + s);
-                n_dq = k1_push(sm.dq, n_dq, lane, to_detail, entry);
-                if (n_dq >= 32u) {                            // leaves both queues below 32
-                    drained = true;
-                    resolve_pending();
-                    const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
-                    n_dq = r & 0xffffu; n_gq = r >> 16;
-                }
-            };
             if (done + n_pass == n_tile_lines) {              // the tile's last pass: the next ticket, its latency hidden
                 if (lane == 0) ticket = (int)atom_inc_u32(&a.st->next_tile);   // behind the parse
                 ticket_taken = true;
             }
-            for (uint32_t l0 = 0; l0 < n_pass; l0 += use_helper ? 64u : 32u) {
+            for (uint32_t l0 = 0; l0 < n_pass; l0 += 32u) {
                 const bool have = l0 + (uint32_t)lane < n_pass;
                 const uint32_t l = have ? l0 + (uint32_t)lane : 0u;
                 const uint32_t code = have ? sm.starts[l] : 0u;
@@ -800,37 +609,26 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                     to_detail = have;
                 }
                 PROF(10);
-                queue_line(to_detail, l, s);
-                PROF(11);
-            }
-            if (use_helper) {
-                pair_sync(warp);                              // the helper is done with the window
-                const uint32_t declined = sm.h_declined;
-                if (declined) {                               // lines its first tier declined: marked in starts[]
-                    for (uint32_t l00 = 0; l00 < n_pass; l00 += 32u) {
-                        const uint32_t l = l00 + (uint32_t)lane;
-                        const uint32_t code = l < n_pass ? sm.starts[l] : 0u;
-                        const bool want = code == 0xffffu ? (declined & H_DECLINED_FIRST) != 0u : (code & START_MARK) != 0u;
-                        uint32_t s = 0;
-                        if (want && code != 0xffffu) {
-                            const uint32_t c = code & START_CODE;
-                            s = (c >> 5) * 16u + (c & 7u) * 4u + ((c >> 3) & 3u) + 1u;
-                        }
-                        queue_line(want, l, s);
-                    }
+                // a line for the second tier is queued with its length (up to the '\n' in front of the next listed
+                // start); the queue is run when 32 wait
+                uint32_t len_hint = 0;
+                if (to_detail && l + 1u < n_pass) {
+                    const uint32_t c1 = sm.starts[l + 1u];
+                    len_hint = (c1 >> 5) * 16u + (c1 & 7u) * 4u + ((c1 >> 3) & 3u) - s;
                 }
+                n_dq = k1_push(sm.dq, n_dq, lane, to_detail, k1_entry(done + l, len_hint, base + s));
+                if (n_dq >= 32u) {                            // leaves both queues below 32
+                    drained = true;
+                    const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, false);
+                    n_dq = r & 0xffffu; n_gq = r >> 16;
+                }
+                PROF(11);
             }
         }
         PROF(12);
         n_lines += n_tile_lines;
     }
-    if (K1_HELPER && !HAS_QUAL) {                             // out of tiles: the helper may leave
-        if (lane == 0) sm.h_flags = H_EXIT;
-        pair_sync(warp);
-    }
     {
-        PROF(0);
-        flush_pending();
         PROF(13);
         const uint32_t r = k1_drain_detail<HAS_QUAL, ALL>(a, sm, cs, lane, n_dq, n_gq, true);
         PROF(14);
@@ -852,10 +650,66 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     }
 }
 
+// ---- per-line results into file order (all-positions mode with line_out) ------------------------------------------
+// k1_tile_prefix_kernel (one block): tile_first[t] = number of lines the tiles in front of t own.
+__global__ void __launch_bounds__(1024) k1_tile_prefix_kernel(const uint32_t *tile_lines, int n_tiles, unsigned long long *tile_first) {
+    __shared__ unsigned long long part[1024];
+    const int tid = (int)threadIdx.x;
+    const int per = (n_tiles + 1023) / 1024;
+    const int lo = min(tid * per, n_tiles), hi = min(lo + per, n_tiles);
+    unsigned long long sum = 0;
+    for (int t = lo; t < hi; t++) sum += tile_lines[t];
+    part[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                      // inclusive scan of the 1024 partial sums
+        const unsigned long long o = tid >= d ? part[tid - d] : 0ull;
+        __syncthreads();
+        part[tid] += o;
+        __syncthreads();
+    }
+    unsigned long long run = part[tid] - sum;
+    for (int t = lo; t < hi; t++) { tile_first[t] = run; run += tile_lines[t]; }
+}
+
+// k1_lines_kernel: one warp per tile copies the tile's row of the staging array to its place in line_out; the blocks
+// behind the last tile scatter the overflow list's entries.
+__global__ void k1_lines_kernel(const uint16_t *stage, const uint32_t *tile_lines, const unsigned long long *tile_first,
+                                int n_tiles, int tile_blocks, const unsigned long long *over, unsigned long long over_cap,
+                                const PileupStatusDev *st, uint16_t *line_out, unsigned long long line_out_cap) {
+    if ((int)blockIdx.x < tile_blocks) {
+        const int tile = (int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+        if (tile >= n_tiles) return;
+        const unsigned long long first = tile_first[tile];
+        uint32_t n = tile_lines[tile];
+        if (n > (uint32_t)K1_STAGE_CAP) n = (uint32_t)K1_STAGE_CAP;
+        const uint16_t *row = stage + (unsigned long long)tile * K1_STAGE_CAP;
+        for (uint32_t i = (uint32_t)lane; i < n; i += 32u)
+            if (first + i < line_out_cap) line_out[first + i] = row[i];
+    } else {
+        unsigned long long n = st->over_used;
+        if (n > over_cap) n = over_cap;                       // (more than fit: the finish kernel reports it)
+        const unsigned long long k = (unsigned long long)((int)blockIdx.x - tile_blocks) * blockDim.x + threadIdx.x;
+        if (k >= n) return;
+        const unsigned long long e = over[k];
+        const unsigned long long slot = tile_first[e >> 32] + ((e >> 16) & 0xffffull);
+        if (slot < line_out_cap) line_out[slot] = (uint16_t)(e & 0xffffull);
+    }
+}
+
+int k1_launch_order(cudaStream_t stream, const PileupArgs &a) {
+    if (!a.line_out || a.n_tiles <= 0) return 0;
+    k1_tile_prefix_kernel<<<1, 1024, 0, stream>>>(a.tile_lines, a.n_tiles, a.tile_first);
+    const int tile_blocks = (a.n_tiles + 7) / 8, over_blocks = (int)((a.over_cap + 255) / 256);
+    k1_lines_kernel<<<tile_blocks + over_blocks, 256, 0, stream>>>(a.stage, a.tile_lines, a.tile_first, a.n_tiles, tile_blocks,
+                                                                   a.over, a.over_cap, a.st, a.line_out, a.line_out_cap);
+    return 2;
+}
+
 // ---- K3: gather the site cells into the consensus row, snplist order (call_consensus.py:187-188); the first
 //      thread also turns the device-side status into the caller's snpgpu_pileup_stats ----------------------
 __global__ void k1_finish_kernel(const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
-                                 uint8_t *row_out, const PileupStatusDev *st, snpgpu_pileup_stats *out) {
+                                 uint8_t *row_out, const PileupStatusDev *st, unsigned long long over_cap,
+                                 snpgpu_pileup_stats *out) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_snp) {
         unsigned long long c = site_cells[snp_unique[k]];
@@ -875,8 +729,10 @@ __global__ void k1_finish_kernel(const unsigned long long *site_cells, const int
         out->n_lines = st->n_lines;
         out->n_parsed = st->n_parsed;
         out->n_general = st->n_general;
-        if (st->arena_overflow) {
-            out->error_offset = st->arena_used;               // bytes of scratch the call needs
+        out->reserved = 0;
+        if (st->arena_overflow || st->over_used > over_cap) {
+            out->error_offset = st->arena_overflow ? st->arena_used : 0ull;      // bytes of splice scratch the call needs
+            out->reserved = st->over_used > over_cap ? (int32_t)((st->over_used + 1023ull) >> 10) : 0;   // overflow entries / 1024
             out->error_code = SNPGPU_E_NOMEM;
         } else if (st->first_error_inv != 0ull) {
             const unsigned long long e = ~st->first_error_inv;
@@ -886,7 +742,6 @@ __global__ void k1_finish_kernel(const unsigned long long *site_cells, const int
             out->error_offset = ~0ull;
             out->error_code = 0;
         }
-        out->reserved = 0;
     }
 }
 
@@ -933,10 +788,11 @@ int k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks) {
 }
 
 int k1_launch_finish(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique, size_t n_snp,
-                     uint8_t *row_out_dev, const PileupStatusDev *st, snpgpu_pileup_stats *stats_dev) {
+                     uint8_t *row_out_dev, const PileupStatusDev *st, unsigned long long over_cap,
+                     snpgpu_pileup_stats *stats_dev) {
     if (!n_snp && !stats_dev) return 0;
     const unsigned grid = (unsigned)((n_snp + 255) / 256);
-    k1_finish_kernel<<<grid ? grid : 1u, 256, 0, stream>>>(site_cells, snp_unique, n_snp, row_out_dev, st, stats_dev);
+    k1_finish_kernel<<<grid ? grid : 1u, 256, 0, stream>>>(site_cells, snp_unique, n_snp, row_out_dev, st, over_cap, stats_dev);
     return 1;
 }
 

@@ -350,6 +350,23 @@ def test_pipelined_host_calls(ctx):
     sites.close()
 
 
+def test_tiny_lines_overflow_the_staging_rows(ctx):
+    """Lines of a few bytes: a 10.5 KiB tile then owns far more lines than its row of the per-line staging array holds
+    (the overflow list, and the call growing it on the second attempt); per-line results still come out in file order."""
+    from snp_pipeline_b200 import _lib
+    rng = random.Random(5)
+    c = "c"
+    body = []
+    for k in range(1, 30001):                                  # "c\t<k>\tA\t0\n": 8-12 bytes, > 1000 lines per tile
+        body.append("%s\t%d\t%s\t0\n" % (c, k, rng.choice("ACGT")))
+    body += [linegen.realistic_line(rng, 30000 + k, c) for k in range(1, 400)]
+    text = "".join(body).encode()
+    snps = [(c, p) for p in sorted(rng.sample(range(1, 30400), 300))]
+    for all_pos in (False, True):
+        _compare(ctx, text, snps, [], PARAM_SETS[1], all_pos)
+        _compare(ctx, text, snps, [], PARAM_SETS[1], all_pos)  # (second call: the list has its grown size from the start)
+
+
 def test_site_table_built_on_device(ctx):
     """snpgpu_sites_create_from_keys_dev (K2's keys -> site table, no host round trip) against the host-built table:
     same consensus rows, same per-line calls, on two contigs."""
