@@ -651,28 +651,46 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
 }
 
 // ---- per-line results into file order (all-positions mode with line_out) ------------------------------------------
-// k1_tile_prefix_kernel (one block): tile_first[t] = number of lines the tiles in front of t own.
-__global__ void __launch_bounds__(1024) k1_tile_prefix_kernel(const uint32_t *tile_lines, int n_tiles, unsigned long long *tile_first) {
-    __shared__ unsigned long long part[1024];
-    const int tid = (int)threadIdx.x;
-    const int per = (n_tiles + 1023) / 1024;
-    const int lo = min(tid * per, n_tiles), hi = min(lo + per, n_tiles);
+// k1_tile_prefix_kernel: block b owns K1_ORDER_TILES consecutive tiles.  It sums the line counts of all tiles in front
+// of its own (coalesced; the counts are a few hundred KB in L2, and summing them again per block is cheaper than a
+// chain of dependent blocks) and scans its own counts -> tile_first[t] = lines the tiles in front of t own.
+constexpr int K1_ORDER_TILES = 512;
+
+__global__ void __launch_bounds__(K1_ORDER_TILES) k1_tile_prefix_kernel(const uint32_t *tile_lines, int n_tiles,
+                                                                        unsigned long long *tile_first) {
+    __shared__ unsigned long long wsum[K1_ORDER_TILES / 32];
+    __shared__ unsigned long long carry_s;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = (int)blockIdx.x * K1_ORDER_TILES;
     unsigned long long sum = 0;
-    for (int t = lo; t < hi; t++) sum += tile_lines[t];
-    part[tid] = sum;
+    for (int t = tid; t < t0; t += K1_ORDER_TILES) sum += tile_lines[t];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) wsum[warp] = sum;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {                      // inclusive scan of the 1024 partial sums
-        const unsigned long long o = tid >= d ? part[tid - d] : 0ull;
-        __syncthreads();
-        part[tid] += o;
-        __syncthreads();
+    if (tid == 0) {
+        unsigned long long c = 0;
+        for (int w = 0; w < K1_ORDER_TILES / 32; w++) c += wsum[w];
+        carry_s = c;
     }
-    unsigned long long run = part[tid] - sum;
-    for (int t = lo; t < hi; t++) { tile_first[t] = run; run += tile_lines[t]; }
+    __syncthreads();
+    const int t = t0 + tid;
+    const uint32_t mine = t < n_tiles ? tile_lines[t] : 0u;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;                        // (carry_s was read from wsum before the barrier above)
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += wsum[w];
+    if (t < n_tiles) tile_first[t] = carry_s + wbase + incl - mine;
 }
 
-// k1_lines_kernel: one warp per tile copies the tile's row of the staging array to its place in line_out; the blocks
-// behind the last tile scatter the overflow list's entries.
+// k1_lines_kernel: one warp per tile copies the tile's row of the staging array to its place in line_out, all its
+// loads in flight together; the blocks behind the last tile scatter the overflow list's entries.
 __global__ void k1_lines_kernel(const uint16_t *stage, const uint32_t *tile_lines, const unsigned long long *tile_first,
                                 int n_tiles, int tile_blocks, const unsigned long long *over, unsigned long long over_cap,
                                 const PileupStatusDev *st, uint16_t *line_out, unsigned long long line_out_cap) {
@@ -683,8 +701,14 @@ __global__ void k1_lines_kernel(const uint16_t *stage, const uint32_t *tile_line
         uint32_t n = tile_lines[tile];
         if (n > (uint32_t)K1_STAGE_CAP) n = (uint32_t)K1_STAGE_CAP;
         const uint16_t *row = stage + (unsigned long long)tile * K1_STAGE_CAP;
-        for (uint32_t i = (uint32_t)lane; i < n; i += 32u)
-            if (first + i < line_out_cap) line_out[first + i] = row[i];
+        uint16_t v[K1_STAGE_CAP / 32];
+#pragma unroll
+        for (int k = 0; k < K1_STAGE_CAP / 32; k++) v[k] = (uint32_t)(lane + 32 * k) < n ? row[lane + 32 * k] : (uint16_t)0;
+#pragma unroll
+        for (int k = 0; k < K1_STAGE_CAP / 32; k++) {
+            const unsigned long long slot = first + (unsigned long long)(lane + 32 * k);
+            if ((uint32_t)(lane + 32 * k) < n && slot < line_out_cap) line_out[slot] = v[k];
+        }
     } else {
         unsigned long long n = st->over_used;
         if (n > over_cap) n = over_cap;                       // (more than fit: the finish kernel reports it)
@@ -698,7 +722,8 @@ __global__ void k1_lines_kernel(const uint16_t *stage, const uint32_t *tile_line
 
 int k1_launch_order(cudaStream_t stream, const PileupArgs &a) {
     if (!a.line_out || a.n_tiles <= 0) return 0;
-    k1_tile_prefix_kernel<<<1, 1024, 0, stream>>>(a.tile_lines, a.n_tiles, a.tile_first);
+    k1_tile_prefix_kernel<<<(a.n_tiles + K1_ORDER_TILES - 1) / K1_ORDER_TILES, K1_ORDER_TILES, 0, stream>>>(a.tile_lines, a.n_tiles,
+                                                                                                          a.tile_first);
     const int tile_blocks = (a.n_tiles + 7) / 8, over_blocks = (int)((a.over_cap + 255) / 256);
     k1_lines_kernel<<<tile_blocks + over_blocks, 256, 0, stream>>>(a.stage, a.tile_lines, a.tile_first, a.n_tiles, tile_blocks,
                                                                    a.over, a.over_cap, a.st, a.line_out, a.line_out_cap);
