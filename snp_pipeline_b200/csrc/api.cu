@@ -423,7 +423,8 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
     const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out_dev != nullptr;
     // per-call scratch that starts as zeros, in one allocation: status | site_cells
-    const size_t z_status = 0, z_cells = 256;
+    const size_t z_status = 0, z_groups = 256;                // status | lines per tile group | site_cells
+    const size_t z_cells = z_groups + (want_lines ? (((size_t)n_tiles / K1_ORDER_TILES + 2) * sizeof(unsigned long long) + 255) & ~(size_t)255 : 0);
     const size_t z_total = z_cells + (sites->n_unique + 1) * sizeof(unsigned long long);
     static_assert(sizeof(PileupStatusDev) <= 64, "status block (the tuning build's counters follow it)");
     CK(ctx->k1_zero.ensure(z_total));
@@ -447,6 +448,7 @@ static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const sn
     a.line_out = want_lines ? line_out_dev : nullptr;
     a.line_out_cap = want_lines ? (unsigned long long)line_out_cap : 0ull;
     a.tile_lines = want_lines ? (uint32_t *)ctx->tile_lines.p : nullptr;
+    a.group_lines = want_lines ? (unsigned long long *)(zb + z_groups) : nullptr;
     a.stage = want_lines ? (uint16_t *)ctx->stage.p : nullptr;
     a.over = want_lines ? (unsigned long long *)ctx->over.p : nullptr;
     a.over_cap = want_lines ? (unsigned long long)ctx->over_want : 0ull;

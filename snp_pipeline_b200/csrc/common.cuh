@@ -40,6 +40,7 @@ constexpr int K1_THREADS  = 32 * K1_WARPS;
 constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
 constexpr int K1_WCAP     = 192;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)
+constexpr int K1_ORDER_TILES = 512;            // tiles per group of the ordering pass (k1_tile_prefix_kernel)
 constexpr int K1_STAGE_CAP = 320;              // per-line results a tile keeps in its row of the staging array (a tile of the
                                                // scan's own path owns at most 32 (K1_LHCAP - 1) + 1 lines; more -> overflow list)
 constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
@@ -58,6 +59,7 @@ struct PileupArgs {
     uint16_t           *line_out;      // null, or one uint16 per line in file order: cell | fail << 8
     unsigned long long  line_out_cap;
     uint32_t           *tile_lines;    // [n_tiles]: lines each tile owns (written by the tile's warp, when line_out)
+    unsigned long long *group_lines;   // zero-initialised: lines per group of K1_ORDER_TILES tiles (atomic adds)
     uint16_t           *stage;         // [n_tiles][K1_STAGE_CAP]: per-line results, tile by tile (when line_out)
     unsigned long long *over;          // overflow list of (tile << 32 | index << 16 | result) for tiles above K1_STAGE_CAP ...
     unsigned long long  over_cap;      // ... its capacity (PileupStatusDev::over_used counts the claims)

@@ -285,7 +285,7 @@ __device__ __noinline__ uint32_t k1_slow_tile(const PileupArgs &a, K1Warp &sm, K
         if (lane >= d) incl += o;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (a.line_out && lane == 0) a.tile_lines[tile] = total;
+    if (a.line_out && lane == 0) { a.tile_lines[tile] = total; atomicAdd(&a.group_lines[tile / K1_ORDER_TILES], (unsigned long long)total); }
     uint32_t idx = incl - cnt, cur = lo;
     bool pending_first = first;
     while (__any_sync(0xffffffffu, cnt > 0u)) {
@@ -565,7 +565,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         const uint32_t n_tile_lines = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t first_idx = incl - cnt;
         // per-line results go to the tile's row of the staging array; its line count is all the ordering pass needs
-        if (a.line_out && lane == 0) a.tile_lines[tile] = n_tile_lines;
+        if (a.line_out && lane == 0) {
+            a.tile_lines[tile] = n_tile_lines;
+            atomicAdd(&a.group_lines[tile / K1_ORDER_TILES], (unsigned long long)n_tile_lines);   // (for k1_tile_prefix_kernel)
+        }
         PROF(6);
         // ---- the warp's list, file order (the first K1_WCAP starts; more -> later passes scan again) -----
         {
@@ -651,19 +654,19 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
 }
 
 // ---- per-line results into file order (all-positions mode with line_out) ------------------------------------------
-// k1_tile_prefix_kernel: block b owns K1_ORDER_TILES consecutive tiles.  It sums the line counts of all tiles in front
-// of its own (coalesced; the counts are a few hundred KB in L2, and summing them again per block is cheaper than a
-// chain of dependent blocks) and scans its own counts -> tile_first[t] = lines the tiles in front of t own.
-constexpr int K1_ORDER_TILES = 512;
+// k1_tile_prefix_kernel: block b owns the b-th group of K1_ORDER_TILES consecutive tiles.  It sums the line totals of the
+// groups in front of its own (the pileup kernel keeps them: one atomic add per tile) and scans its own tiles' counts
+// -> tile_first[t] = lines the tiles in front of t own.
 
-__global__ void __launch_bounds__(K1_ORDER_TILES) k1_tile_prefix_kernel(const uint32_t *tile_lines, int n_tiles,
+__global__ void __launch_bounds__(K1_ORDER_TILES) k1_tile_prefix_kernel(const uint32_t *tile_lines,
+                                                                        const unsigned long long *group_lines, int n_tiles,
                                                                         unsigned long long *tile_first) {
     __shared__ unsigned long long wsum[K1_ORDER_TILES / 32];
     __shared__ unsigned long long carry_s;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = (int)blockIdx.x * K1_ORDER_TILES;
-    unsigned long long sum = 0;
-    for (int t = tid; t < t0; t += K1_ORDER_TILES) sum += tile_lines[t];
+    unsigned long long sum = 0;                               // lines of the groups of K1_ORDER_TILES tiles in front of this one
+    for (int g = tid; g < (int)blockIdx.x; g += K1_ORDER_TILES) sum += group_lines[g];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     if (lane == 0) wsum[warp] = sum;
@@ -722,8 +725,8 @@ __global__ void k1_lines_kernel(const uint16_t *stage, const uint32_t *tile_line
 
 int k1_launch_order(cudaStream_t stream, const PileupArgs &a) {
     if (!a.line_out || a.n_tiles <= 0) return 0;
-    k1_tile_prefix_kernel<<<(a.n_tiles + K1_ORDER_TILES - 1) / K1_ORDER_TILES, K1_ORDER_TILES, 0, stream>>>(a.tile_lines, a.n_tiles,
-                                                                                                          a.tile_first);
+    k1_tile_prefix_kernel<<<(a.n_tiles + K1_ORDER_TILES - 1) / K1_ORDER_TILES, K1_ORDER_TILES, 0, stream>>>(
+        a.tile_lines, a.group_lines, a.n_tiles, a.tile_first);
     const int tile_blocks = (a.n_tiles + 7) / 8, over_blocks = (int)((a.over_cap + 255) / 256);
     k1_lines_kernel<<<tile_blocks + over_blocks, 256, 0, stream>>>(a.stage, a.tile_lines, a.tile_first, a.n_tiles, tile_blocks,
                                                                    a.over, a.over_cap, a.st, a.line_out, a.line_out_cap);
