@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     const int n_gwarps = gridDim.x * K1_WARPS;
     ContigCache cc;
     contig_cache_load(a.sites, 0, sm.cname, sm.cmask, K1_NAMEW, &cc);   // every lane writes the same words
+    static_assert(K1_PAD == 32, "one sentinel byte per lane");
+    sm.buf[K1_TILE + K1_LOOK + lane] = (uint8_t)'\n';        // the '\n' sentinels behind a whole window: no copy ever reaches them
     __syncwarp();
     int ticket = 0;                                           // lane 0: the next tile, when ticket_taken
     bool drained = false;                                     // queued lines ran since the contig cache was last checked
@@ -442,8 +444,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 if (nb) bulk_prefetch_l2(a.text + nbase, nb);
             }
         }
-        for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)
-            sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
+        if (wlen != (uint32_t)(K1_TILE + K1_LOOK)) {          // the text's last windows: the bytes behind the last whole 16 and
+            for (uint32_t j = bulk + (uint32_t)lane; j < wlen + (uint32_t)K1_PAD; j += 32u)     // the sentinels behind them
+                sm.buf[j] = j < wlen ? a.text[base + j] : (uint8_t)'\n';
+        }                                                     // (a whole window ends at the sentinels written once, below)
         PROF(1);
         PROF(2);
         if (n_dq >= (uint32_t)K1_DRAIN_AT) {                  // queued lines, while this window loads
