@@ -33,12 +33,16 @@ struct PileupStatusDev {
 constexpr int K1_LANE_CHUNKS = K1_CFG_CHUNKS;             // 16-byte chunks one lane scans for newlines ...
 constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
 constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
-constexpr int K1_LOOK     = 896;               // extra bytes staged so that the last owned line is complete
+#ifndef K1_CFG_LOOK
+#define K1_CFG_LOOK 896
+#define K1_CFG_WCAP 192
+#endif
+constexpr int K1_LOOK     = K1_CFG_LOOK;              // extra bytes staged so that the last owned line is complete
 constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
 constexpr int K1_WARPS    = 4;                 // independent warps per CTA
 constexpr int K1_THREADS  = 32 * K1_WARPS;
 constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
-constexpr int K1_WCAP     = 192;               // line starts a warp lists per pass (more -> another pass)
+constexpr int K1_WCAP     = K1_CFG_WCAP;               // line starts a warp lists per pass (more -> another pass)
 constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)
 constexpr int K1_ORDER_TILES = 512;            // tiles per group of the ordering pass (k1_tile_prefix_kernel)
 constexpr int K1_STAGE_CAP = 320;              // per-line results a tile keeps in its row of the staging array (a tile of the
