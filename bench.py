@@ -301,7 +301,7 @@ def run_reference(args, rank):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         pass
-    n_ref = max(1, min(cores, 16, args.samples))
+    n_ref = max(1, min(cores, 32, args.samples))             # one sample per host thread (32 x 0.46 GB of text at most)
     ctx = _lib.Context(0)
     cap = args.genome_len * 112 + 4096
     scratch = torch.empty(cap, dtype=torch.uint8, device="cuda")
