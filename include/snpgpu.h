@@ -235,7 +235,7 @@ typedef struct {
     uint32_t mean_depth;       /* ~Poisson-shaped, clipped to [0, 60]                                */
     uint32_t n_pool_sites;     /* size of the global variant-site pool (same for every sample)       */
     float    site_carry_prob;  /* probability that this sample carries a given pool site             */
-    float    reserved;
+    float    indel_line_rate;  /* fraction of lines that carry one indel token; 0 = the default 0.001  */
 } snpgpu_synth_spec;
 
 int snpgpu_synth_pileup_dev(snpgpu_ctx *ctx, const snpgpu_synth_spec *spec, const char *contig_name,

@@ -16,7 +16,7 @@ ctx = _lib.Context(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
-spec = _lib.SynthSpec(20261017, 0, G, 24, G // 100, 0.05, 0.0)
+spec = _lib.SynthSpec(20261017, 0, G, 24, G // 100, 0.05, float(os.environ.get("INDEL_RATE", "0")))   # 0: the default 0.1 % of lines
 cap = G * 112 + 4096
 buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
 n = ctx.synth_pileup_dev(spec, "gi|0000000|ref|SYN_5000K.1|", buf.data_ptr(), cap)

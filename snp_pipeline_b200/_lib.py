@@ -56,7 +56,7 @@ assert VCF_RECORD_DTYPE.itemsize == 64 and VCF_ALT_DTYPE.itemsize == 16
 class SynthSpec(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("sample", ctypes.c_uint32), ("genome_len", ctypes.c_uint32),
                 ("mean_depth", ctypes.c_uint32), ("n_pool_sites", ctypes.c_uint32),
-                ("site_carry_prob", ctypes.c_float), ("reserved", ctypes.c_float)]
+                ("site_carry_prob", ctypes.c_float), ("indel_line_rate", ctypes.c_float)]
 
 
 def make_params(min_base_qual=0, min_cons_freq=0.6, min_cons_depth=1, min_cons_strand_depth=0,

@@ -20,6 +20,7 @@ struct SynthArgs {
     uint32_t sample, genome_len, mean_depth;
     uint32_t pool_thresh;      // a position is a pool site iff hash32(pool) < pool_thresh
     uint32_t carry_thresh;     // a sample carries a pool site iff hash32(carry) < carry_thresh
+    uint32_t indel_thresh;     // a line carries an indel token iff its 24-bit draw < indel_thresh (0.1 % by default)
     int      name_len;
     char     name[64];
 };
@@ -85,7 +86,7 @@ SNP_HD uint32_t synth_line(const SynthArgs &a, uint32_t pos, uint8_t *out) {
     PUT('\t');
     const bool variant = synth_carries(a, pos);
     const unsigned alt = synth_alt_base(a.seed, pos);
-    const bool has_indel = (uint32_t)((h0 >> 24) & 0xffffffu) < 16777u;   // 0.1 %
+    const bool has_indel = (uint32_t)((h0 >> 24) & 0xffffffu) < a.indel_thresh;
     const uint32_t indel_at = (uint32_t)((h0 >> 48) % depth);
     for (uint32_t r = 0; r < depth; r++) {
         const uint64_t h = draw(a.seed, a.sample, pos, 16 + r);
@@ -164,6 +165,9 @@ static SynthArgs make_args(const snpgpu_synth_spec &spec, const char *contig_nam
     if (cp < 0) cp = 0;
     if (cp > 1) cp = 1;
     a.carry_thresh = (uint32_t)(cp * 4294967295.0);
+    double ir = spec.indel_line_rate > 0 ? spec.indel_line_rate : 0.001;       // lines with one indel token
+    if (ir > 1) ir = 1;
+    a.indel_thresh = (uint32_t)(ir * 16777216.0);
     if (contig_name) {
         size_t L = strlen(contig_name);
         if (L > 63) L = 63;
