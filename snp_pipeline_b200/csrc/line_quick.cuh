@@ -9,13 +9,15 @@
 // That is >= 98 % of the lines of a real pileup.  This parser computes exactly those four numbers with SWAR
 // masks, four bytes per step and no symbol-dependent branch, validates every byte of the line on the way
 // (separators, digits, printable quality string as long as the stripped bases -- the zip() of pileup.py:248),
-// and returns ST_DETAIL for anything else: another winner possible, an indel token, a "^^" chain, a trailing
-// '^', an odd separator, "\r\n", depth 0, a contig other than the hinted one ...  ST_DETAIL has no side
-// effects; the caller hands the line to line_fast.cuh (exact tallies) and, from there, to line_general.cuh.
+// skips indel tokens of up to 999 bases in a second look at the column (only lines that showed a '+' / '-'),
+// and returns ST_DETAIL for anything else: another winner possible, a "^^" chain, a trailing '^', a malformed
+// or longer indel token, an odd separator, "\r\n", depth 0, a contig other than the hinted one ...  ST_DETAIL
+// has no side effects; the caller hands the line to line_fast.cuh (exact tallies) and, from there, to line_general.cuh.
 //
 // Precondition (the kernel checks it per tile): no byte >= 0x80 in the staged window, so byte lanes never
 // carry into each other.  buf is 4-byte aligned with '\n' sentinels behind `limit`.
 #pragma once
+#include <type_traits>
 #include "line_fast.cuh"
 
 namespace snpgpu {
@@ -216,29 +218,72 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     WordReader rd;
     rd.seek(buf, i);
     const uint32_t refb = (ref | 0x20u) * 0x01010101u;
-    uint32_t a_rem = 0, a_dc = 0, a_dot = 0;           // 128 x (removed bytes, kept '.'/',', kept '.')
-    uint32_t anomaly = 0, prevcar = 0, nfull = 0;
-    uint32_t w, c;
-    for (;;) {
-        w = rd.next();
-        c = w + 0x5f5f5f5fu;                           // bit 7 clear <-> byte < 0x21
-        if (~c & H) break;
-        const uint32_t in = (w + 0x55555555u) & ~(w + 0x51515151u) & H;        // + , - .
-        const uint32_t s7 = w << 7;                                            // bit 0 -> bit 7: '+' and '-'
-        const uint32_t car = ~((w ^ 0x5e5e5e5eu) + K) & H;                     // '^'
-        const uint32_t dol = ~((w ^ 0x24242424u) + K) & H;                     // '$'
-        const uint32_t part = funnel_l8(prevcar, car);                         // the byte after a '^'
-        const uint32_t refm = ~(((w | 0x20202020u) ^ refb) + K) & H;           // the reference letter, either case
-        anomaly |= (in & s7 & ~part) | (car & part) | refm;
-        const uint32_t dck = in & ~s7 & ~part;
-        a_rem = flag_sum(car | part | dol, a_rem);
-        a_dc = flag_sum(dck, a_dc);
-        a_dot = flag_sum(dck & (w << 6), a_dot);                               // bit 1 -> bit 7: '.' not ','
-        prevcar = car;
-        nfull++;
-    }
-    uint32_t bases_len;
-    {   // the word that holds the separator: the same, restricted to the bytes in front of it
+    uint32_t a_rem, a_dc, a_dot;                       // 128 x (removed bytes, kept '.'/',', kept '.')
+    uint32_t anomaly = 0, signs = 0, prevcar = 0;
+    uint32_t wpos;                                     // offset of the word being looked at
+    uint32_t bases_len = 0;
+    // An indel token [+-]<n><n letters> (pileup.py:315-320) whose sign is the lowest flag of `sign` in the word at wpos:
+    // the bytes in front of it are counted like any others, the token is skipped byte-wise (1..3 digits, a sequence of
+    // letters / '*' as line_fast.cuh takes it) and the word reader starts again behind it.  false: not for this tier.
+    auto skip_indel = [&](uint32_t w, uint32_t sign, uint32_t in, uint32_t s7, uint32_t car, uint32_t dol, uint32_t part,
+                          uint32_t refm) -> bool {
+        const uint32_t fs = sign & (0u - sign);
+        const uint32_t v2 = (fs - 1u) & H;                                     // the bytes in front of the sign
+        const uint32_t car2 = car & v2, part2 = part & v2, dck2 = in & ~s7 & ~part & v2;
+        anomaly |= (car2 & part2) | (refm & v2);
+        a_rem = flag_sum(car2 | part2 | (dol & v2), a_rem);
+        a_dc = flag_sum(dck2, a_dc);
+        a_dot = flag_sum(dck2 & (w << 6), a_dot);
+        uint32_t k = wpos + ((uint32_t)ctz32(fs) >> 3) + 1u, n = 0, nd = 0;
+        while (nd < 3u && (unsigned)buf[k] - '0' < 10u) { n = n * 10u + ((unsigned)buf[k] - '0'); k++; nd++; }
+        if (nd == 0u || (unsigned)buf[k] - '0' < 10u || k + n > limit) return false;   // a bare sign, a long number
+        for (uint32_t x = 0; x < n; x++) {
+            const unsigned ch = buf[k + x];
+            if ((ch | 0x20u) - 'a' >= 26u && ch != '*') return false;
+        }
+        a_rem += 128u * (1u + nd + n);
+        wpos = k + n;
+        rd.seek(buf, wpos);
+        prevcar = 0;
+        return true;
+    };
+    // One look at the column.  The first look only notes '+' / '-' (no branch per word: the loop is latency-bound); a
+    // line that showed one and nothing else odd is looked at again with the tokens skipped.  false: not for this tier.
+    auto look = [&](auto with_indels) -> bool {
+        constexpr bool INDEL = decltype(with_indels)::value;
+        rd.seek(buf, i);
+        a_rem = a_dc = a_dot = 0;
+        anomaly = signs = prevcar = 0;
+        wpos = i;
+        uint32_t w, c;
+        for (;;) {
+            w = rd.next();
+            c = w + 0x5f5f5f5fu;                       // bit 7 clear <-> byte < 0x21
+            if (~c & H) break;
+            const uint32_t in = (w + 0x55555555u) & ~(w + 0x51515151u) & H;    // + , - .
+            const uint32_t s7 = w << 7;                                        // bit 0 -> bit 7: '+' and '-'
+            const uint32_t car = ~((w ^ 0x5e5e5e5eu) + K) & H;                 // '^'
+            const uint32_t dol = ~((w ^ 0x24242424u) + K) & H;                 // '$'
+            const uint32_t part = funnel_l8(prevcar, car);                     // the byte after a '^'
+            const uint32_t refm = ~(((w | 0x20202020u) ^ refb) + K) & H;       // the reference letter, either case
+            const uint32_t sign = in & s7 & ~part;                             // '+' / '-' that is not a '^' partner
+            if constexpr (INDEL) {
+                if (sign) {
+                    if (!skip_indel(w, sign, in, s7, car, dol, part, refm)) return false;
+                    continue;
+                }
+            } else {
+                signs |= sign;
+            }
+            anomaly |= (car & part) | refm;
+            const uint32_t dck = in & ~s7 & ~part;
+            a_rem = flag_sum(car | part | dol, a_rem);
+            a_dc = flag_sum(dck, a_dc);
+            a_dot = flag_sum(dck & (w << 6), a_dot);                           // bit 1 -> bit 7: '.' not ','
+            prevcar = car;
+            wpos += 4u;
+        }
+        // the word that holds the separator: the same, restricted to the bytes in front of it
         const uint32_t low = ~c & H;
         const uint32_t first = low & (0u - low);
         const uint32_t valid = (first - 1u) & H;
@@ -249,14 +294,20 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
         const uint32_t dol = ~((w ^ 0x24242424u) + K) & valid;
         const uint32_t part = funnel_l8(prevcar, car);                         // may reach the separator itself
         const uint32_t refm = ~(((w | 0x20202020u) ^ refb) + K) & valid;
-        anomaly |= (in & s7 & ~part) | (car & part) | refm | (part & first);   // "^" + separator: trailing '^'
+        const uint32_t sign = in & s7 & ~part;
+        // (with tokens skipped, a sign here is the 1-in-4 case "+1A" + separator in one word, or malformed: next tier)
+        if constexpr (INDEL) anomaly |= sign; else signs |= sign;
+        anomaly |= (car & part) | refm | (part & first);                       // "^" + separator: trailing '^'
         const uint32_t dck = in & ~s7 & ~part;
         a_rem = flag_sum((car | part | dol) & valid, a_rem);
         a_dc = flag_sum(dck, a_dc);
         a_dot = flag_sum(dck & (w << 6), a_dot);
         if (((w >> (8u * j)) & 0xffu) != '\t') anomaly |= H;                   // the column ends in a tab
-        bases_len = 4u * nfull + j;
-    }
+        bases_len = wpos + j - i;
+        return true;
+    };
+    look(std::false_type{});
+    if (signs && !look(std::true_type{})) return ST_DETAIL;   // (what else the first look flagged may lie in a token)
     if (anomaly || bases_len == 0) return ST_DETAIL;
     const uint32_t nb = bases_len - (a_rem >> 7);      // length of the stripped string
     const uint32_t q0 = i + bases_len + 1u;
@@ -266,7 +317,7 @@ SNP_HD int quick_line(const uint8_t *buf, uint32_t s, uint32_t limit, const Site
     uint32_t acc = H;
 #pragma unroll 2
     for (uint32_t k = nb >> 2; k > 0; k--) acc &= rd.next() + 0x5f5f5f5fu;
-    w = rd.next();
+    const uint32_t w = rd.next();
     const uint32_t r = nb & 3u;
     const uint32_t expect = 0x80u << (8u * r);
     const uint32_t low = ~(w + 0x5f5f5f5fu) & H;

@@ -266,3 +266,38 @@ def test_lambda_golden(sim, golden_dir):
                 assert orc.fasta_text(s, row.decode()) == open(os.path.join(sdir, "consensus%s.fasta" % branch)).read()
                 if all_pos:
                     assert c[2] < 200, "lambda pileups should stay on the fast path (got %d general lines)" % c[2]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_indel_tokens_in_the_first_tier(sim, seed):
+    """Lines with indel tokens [+-]<n><n letters> (samtools' shape, 1..3 digits, several per line, next to '^x' and '$',
+    at the start and at the end of the column): decided by the first-tier parser, exactly."""
+    rng = random.Random(7000 + seed)
+    n = 1500
+    lines = [linegen.realistic_line(rng, 1 + k, indel_rate=0.08) for k in range(n)]
+    for k in range(0, n, 97):                                          # hand-made corners
+        ref = rng.choice("ACGT")
+        seq = "".join(rng.choice("ACGTNacgtn") for _ in range(12))
+        bases = rng.choice(["+2AC....,,,,", "....,,,,-3acg", ".+1A,-1c.^K.$,,", ".-12" + seq + ",,..", ".+10" + seq[:10] + ".,"])
+        nb = len(orc_strip(bases))
+        lines[k] = "%s\t%d\t%s\t%d\t%s\t%s\n" % (linegen.CHROM, 1 + k, ref, nb, bases, "".join(chr(33 + rng.randint(13, 39)) for _ in range(nb)))
+    text = "".join(lines).encode()
+    snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 150))]
+    for all_pos in (False, True):
+        c = _compare(sim, text, snps, [], PARAM_SETS[seed % 4], all_pos)
+        if all_pos and PARAM_SETS[seed % 4][0] <= 0:
+            assert c[5] > c[1] * 0.9, "the first-tier parser should decide the indel lines too (%d of %d)" % (c[5], c[1])
+
+
+def orc_strip(bases):
+    """pileup.py:276-325 for well-formed input: '^x' pairs, then indel tokens with their sequences, then '$'."""
+    import re
+    s = re.sub(r"\^.", "", bases)
+    out, i = [], 0
+    while i < len(s):
+        m = re.match(r"[+-](\d+)", s[i:])
+        if m:
+            i += len(m.group(0)) + int(m.group(1))
+        else:
+            out.append(s[i]); i += 1
+    return "".join(out).replace("$", "")
