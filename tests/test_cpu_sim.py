@@ -289,6 +289,46 @@ def test_indel_tokens_in_the_first_tier(sim, seed):
             assert c[5] > c[1] * 0.9, "the first-tier parser should decide the indel lines too (%d of %d)" % (c[5], c[1])
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_indel_token_corners(sim, seed):
+    """Indel tokens the first tier must either decide exactly or hand on: at every byte alignment against the column's
+    end, bare signs, counts of 0 / 4 digits / more bases than the column holds, sequences with non-letters, signs behind
+    '^', tokens back to back -- whatever the tier, the result is the oracle's."""
+    rng = random.Random(9100 + seed)
+    pieces = ["+1A", "-1c", "+2AC", "-3acg", "+10ACGTACGTAC", "-999" + "a" * 999, "+1000" + "C" * 1000, "+", "-", "+0", "-0A",
+              "+1", "+2A", "+3AC", "+1.", "-2,.", "+1*", "-2*a", "^+", "^-", "^+1A", "+1^", "-1$", "+1A5", "+01A", "+1A+1C", "-1a-2cc",
+              "+1A$", "$+1A", "^K+1A", "+2^K", "*", "+1N", "-1n", "+12ACGTNacgtn*"]
+    n = 900
+    lines = []
+    for k in range(n):
+        ref = rng.choice("ACGT")
+        parts = [rng.choice(".,") * rng.randint(0, 9) for _ in range(rng.randint(1, 4))]
+        for x in range(len(parts) - (0 if rng.random() < 0.5 else 1)):          # a token between runs, sometimes last
+            parts[x] += rng.choice(pieces)
+        if rng.random() < 0.3:
+            parts.insert(0, rng.choice(pieces))                                # ... and sometimes first
+        bases = "".join(parts)
+        nb = len(orc_strip(bases)) if rng.random() < 0.8 else rng.randint(0, 12)
+        qual = "".join(chr(33 + rng.randint(13, 39)) for _ in range(nb))
+        lines.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (linegen.CHROM, 1 + k, ref, max(nb, 1), bases, qual))
+    ps = PARAM_SETS[seed % len(PARAM_SETS)]
+    op = orc.make_params(*ps)
+    good, n_bad = [], 0
+    for k, line in enumerate(lines):                   # lines the reference stops at (a bare sign: int("")): one by one
+        try:
+            orc.pileup_consensus(line.encode(), [], [], op, parse_all=True, want_lines=True)
+            good.append(line)
+        except orc.OracleError:
+            n_bad += 1
+            _compare(sim, line.encode(), [(linegen.CHROM, 1 + k)], [], ps, True)
+    assert len(good) > n // 2 and n_bad > 10
+    text = "".join(good).encode()
+    snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 200))]
+    for all_pos in (False, True):
+        c = _compare(sim, text, snps, [], ps, all_pos)
+        assert c[0] == (len(good) if all_pos else c[0])
+
+
 def orc_strip(bases):
     """pileup.py:276-325 for well-formed input: '^x' pairs, then indel tokens with their sequences, then '$'."""
     import re
