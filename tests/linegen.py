@@ -125,3 +125,41 @@ def pileup_text(seed, n_lines, chrom=CHROM, nasty=0.0, start=1, gaps=0.0, sites=
         if gaps and rng.random() < gaps:
             pos += rng.randint(1, 50)
     return "".join(out)
+
+
+def strip_bases(bases):
+    """pileup.py:276-325 for well-formed input: '^x' pairs, then indel tokens with their sequences, then '$'."""
+    import re
+    s = re.sub(r"\^.", "", bases)
+    out, i = [], 0
+    while i < len(s):
+        m = re.match(r"[+-](\d+)", s[i:])
+        if m:
+            i += len(m.group(0)) + int(m.group(1))
+        else:
+            out.append(s[i])
+            i += 1
+    return "".join(out).replace("$", "")
+
+
+INDEL_PIECES = ["+1A", "-1c", "+2AC", "-3acg", "+10ACGTACGTAC", "-999" + "a" * 999, "+1000" + "C" * 1000, "+", "-", "+0", "-0A",
+                "+1", "+2A", "+3AC", "+1.", "-2,.", "+1*", "-2*a", "^+", "^-", "^+1A", "+1^", "-1$", "+1A5", "+01A", "+1A+1C",
+                "-1a-2cc", "+1A$", "$+1A", "^K+1A", "+2^K", "*", "+1N", "-1n", "+12ACGTNacgtn*"]
+
+
+def indel_corner_lines(rng, n):
+    """n lines (positions 1..n) of '.'/',' runs with well- and ill-formed indel tokens between, before and behind them,
+    so that the tokens meet the column's end at every byte alignment; some with a quality string of another length."""
+    lines = []
+    for k in range(n):
+        ref = rng.choice("ACGT")
+        parts = [rng.choice(".,") * rng.randint(0, 9) for _ in range(rng.randint(1, 4))]
+        for x in range(len(parts) - (0 if rng.random() < 0.5 else 1)):          # a token between runs, sometimes last
+            parts[x] += rng.choice(INDEL_PIECES)
+        if rng.random() < 0.3:
+            parts.insert(0, rng.choice(INDEL_PIECES))                          # ... and sometimes first
+        bases = "".join(parts)
+        nb = len(strip_bases(bases)) if rng.random() < 0.8 else rng.randint(0, 12)
+        qual = "".join(chr(33 + rng.randint(13, 39)) for _ in range(nb))
+        lines.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (CHROM, 1 + k, ref, max(nb, 1), bases, qual))
+    return lines

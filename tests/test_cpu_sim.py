@@ -279,7 +279,7 @@ def test_indel_tokens_in_the_first_tier(sim, seed):
         ref = rng.choice("ACGT")
         seq = "".join(rng.choice("ACGTNacgtn") for _ in range(12))
         bases = rng.choice(["+2AC....,,,,", "....,,,,-3acg", ".+1A,-1c.^K.$,,", ".-12" + seq + ",,..", ".+10" + seq[:10] + ".,"])
-        nb = len(orc_strip(bases))
+        nb = len(linegen.strip_bases(bases))
         lines[k] = "%s\t%d\t%s\t%d\t%s\t%s\n" % (linegen.CHROM, 1 + k, ref, nb, bases, "".join(chr(33 + rng.randint(13, 39)) for _ in range(nb)))
     text = "".join(lines).encode()
     snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 150))]
@@ -295,22 +295,8 @@ def test_indel_token_corners(sim, seed):
     end, bare signs, counts of 0 / 4 digits / more bases than the column holds, sequences with non-letters, signs behind
     '^', tokens back to back -- whatever the tier, the result is the oracle's."""
     rng = random.Random(9100 + seed)
-    pieces = ["+1A", "-1c", "+2AC", "-3acg", "+10ACGTACGTAC", "-999" + "a" * 999, "+1000" + "C" * 1000, "+", "-", "+0", "-0A",
-              "+1", "+2A", "+3AC", "+1.", "-2,.", "+1*", "-2*a", "^+", "^-", "^+1A", "+1^", "-1$", "+1A5", "+01A", "+1A+1C", "-1a-2cc",
-              "+1A$", "$+1A", "^K+1A", "+2^K", "*", "+1N", "-1n", "+12ACGTNacgtn*"]
     n = 900
-    lines = []
-    for k in range(n):
-        ref = rng.choice("ACGT")
-        parts = [rng.choice(".,") * rng.randint(0, 9) for _ in range(rng.randint(1, 4))]
-        for x in range(len(parts) - (0 if rng.random() < 0.5 else 1)):          # a token between runs, sometimes last
-            parts[x] += rng.choice(pieces)
-        if rng.random() < 0.3:
-            parts.insert(0, rng.choice(pieces))                                # ... and sometimes first
-        bases = "".join(parts)
-        nb = len(orc_strip(bases)) if rng.random() < 0.8 else rng.randint(0, 12)
-        qual = "".join(chr(33 + rng.randint(13, 39)) for _ in range(nb))
-        lines.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (linegen.CHROM, 1 + k, ref, max(nb, 1), bases, qual))
+    lines = linegen.indel_corner_lines(rng, n)
     ps = PARAM_SETS[seed % len(PARAM_SETS)]
     op = orc.make_params(*ps)
     good, n_bad = [], 0
@@ -327,17 +313,3 @@ def test_indel_token_corners(sim, seed):
     for all_pos in (False, True):
         c = _compare(sim, text, snps, [], ps, all_pos)
         assert c[0] == (len(good) if all_pos else c[0])
-
-
-def orc_strip(bases):
-    """pileup.py:276-325 for well-formed input: '^x' pairs, then indel tokens with their sequences, then '$'."""
-    import re
-    s = re.sub(r"\^.", "", bases)
-    out, i = [], 0
-    while i < len(s):
-        m = re.match(r"[+-](\d+)", s[i:])
-        if m:
-            i += len(m.group(0)) + int(m.group(1))
-        else:
-            out.append(s[i]); i += 1
-    return "".join(out).replace("$", "")

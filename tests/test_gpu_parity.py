@@ -119,6 +119,33 @@ def test_realistic_text(ctx, seed):
 
 
 @pytest.mark.parametrize("seed", range(3))
+def test_indel_token_corners(ctx, seed):
+    """Well- and ill-formed indel tokens at every alignment against the column's end (tests/linegen.py): the lines the
+    reference parses in one text, a few of those it stops at (a bare sign: int("")) alone and behind good lines."""
+    rng = random.Random(9100 + seed)
+    n = 900
+    lines = linegen.indel_corner_lines(rng, n)
+    ps = PARAM_SETS[seed % len(PARAM_SETS)]
+    op = orc.make_params(*ps)
+    good, bad = [], []
+    for k, line in enumerate(lines):
+        try:
+            orc.pileup_consensus(line.encode(), [], [], op, parse_all=True, want_lines=True)
+            good.append(line)
+        except orc.OracleError:
+            bad.append((k, line))
+    assert len(good) > n // 2 and len(bad) > 10
+    snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 200))]
+    text = "".join(good).encode()
+    for all_pos in (False, True):
+        st = _compare(ctx, text, snps, [], ps, all_pos)
+        assert st.n_lines == len(good)
+    for k, line in bad[:4]:
+        assert _compare(ctx, line.encode(), [(linegen.CHROM, 1 + k)], [], ps, True) is None
+        assert _compare(ctx, ("".join(good[:300]) + line + "".join(good[300:400])).encode(), snps, [], ps, True) is None
+
+
+@pytest.mark.parametrize("seed", range(3))
 def test_header_shapes(ctx, seed):
     """Contig names of every length, positions of 1..10 digits, depths of 1..4 digits (the word-wise header parse)."""
     from test_cpu_sim import header_shapes_text
