@@ -1,5 +1,5 @@
 """Profiling driver: one synthetic 5 Mbp sample resident in HBM, K1 (all-positions mode) launched a few times.
-Usage (on the GPU box):  ncu --set full --clock-control none --import-source on -k regex:k1_pileup -s 2 -c 1 \
+Usage (on the GPU box):  ncu --set full --clock-control none --import-source on -k regex:k1_pileup_kernel -s 2 -c 1 \
                              -o gpurun_out/k1 python profiles/run_k1.py [sites|all] [n_launches]"""
 import os
 import sys
@@ -22,13 +22,16 @@ buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
 n = ctx.synth_pileup_dev(spec, "gi|0000000|ref|SYN_5000K.1|", buf.data_ptr(), cap)
 pos = ctx.synth_sample_sites(spec)
 sites = _lib.Sites.from_arrays(ctx, ["gi|0000000|ref|SYN_5000K.1|"], np.zeros(pos.size, np.int32), pos.astype(np.int64))
-row = torch.empty(max(pos.size, 1), dtype=torch.uint8, device="cuda")
-lines = torch.empty(G + 64, dtype=torch.int16, device="cuda")
-stats = torch.zeros(5, dtype=torch.int64, device="cuda")
+B = int(os.environ.get("BATCH", "8"))                     # samples per launch (the same text, separate outputs)
+row = torch.empty((B, max(pos.size, 1)), dtype=torch.uint8, device="cuda")
+lines = torch.empty((B, G + 64), dtype=torch.int16, device="cuda")
+stats = torch.zeros((B, 5), dtype=torch.int64, device="cuda")
 p = _lib.make_params(min_cons_depth=3)
 ctx.enable_timing(True)
+batch = [(buf.data_ptr(), n, row[i].data_ptr(), lines[i].data_ptr(), G + 64, stats[i].data_ptr()) for i in range(B)]
 for _ in range(n_launch):
-    ctx.pileup_consensus_dev(buf.data_ptr(), n, sites, p, mode, row.data_ptr(), lines.data_ptr(), G + 64, stats.data_ptr())
+    ctx.pileup_consensus_batch_dev(batch, sites, p, mode)
 torch.cuda.synchronize()
 ms, k = ctx.kernel_time(0)
-print("text bytes %d, K1 avg %.3f ms over %d launches -> %.1f GB/s; stats %s" % (n, ms / k, k, n / (ms / k) / 1e6, stats.tolist()))
+per = ms / (k * B)
+print("text bytes %d, K1 avg %.4f ms per sample over %d launches of %d samples -> %.1f GB/s; stats %s" % (n, per, k, B, n / per / 1e6, stats[0].tolist()))

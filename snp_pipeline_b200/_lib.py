@@ -23,7 +23,7 @@ EXPORTS = [
     "snpgpu_sync", "snpgpu_host_alloc", "snpgpu_host_free", "snpgpu_launch_count", "snpgpu_enable_timing",
     "snpgpu_kernel_time", "snpgpu_sites_create", "snpgpu_sites_create_from_keys_dev",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
-    "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end",
+    "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end", "snpgpu_pileup_consensus_batch_dev",
     "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_reference_bases",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
@@ -40,6 +40,12 @@ class Params(ctypes.Structure):
 class PileupStats(ctypes.Structure):
     _fields_ = [("n_lines", ctypes.c_uint64), ("n_parsed", ctypes.c_uint64), ("n_general", ctypes.c_uint64),
                 ("error_offset", ctypes.c_uint64), ("error_code", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class PileupSample(ctypes.Structure):
+    """snpgpu_pileup_sample: one sample of snpgpu_pileup_consensus_batch_dev (device pointers)."""
+    _fields_ = [("text_dev", ctypes.c_void_p), ("nbytes", ctypes.c_size_t), ("row_out_dev", ctypes.c_void_p),
+                ("line_out_dev", ctypes.c_void_p), ("line_out_cap", ctypes.c_size_t), ("stats_dev", ctypes.c_void_p)]
 
 
 VCF_HAS_DEPTH, VCF_FIRST_IS_REF = 1, 2
@@ -126,6 +132,8 @@ def load():
     L.snpgpu_pileup_consensus_end.argtypes = [vp, ctypes.c_int]
     L.snpgpu_pileup_consensus_dev.restype = ctypes.c_int
     L.snpgpu_pileup_consensus_dev.argtypes = [vp, vp, sz, vp, P(Params), ctypes.c_int, vp, vp, sz, vp]
+    L.snpgpu_pileup_consensus_batch_dev.restype = ctypes.c_int
+    L.snpgpu_pileup_consensus_batch_dev.argtypes = [vp, P(PileupSample), sz, vp, P(Params), ctypes.c_int]
     L.snpgpu_normalize_newlines_dev.restype = ctypes.c_int
     L.snpgpu_normalize_newlines_dev.argtypes = [vp, vp, sz]
     L.snpgpu_reference_bases.restype = ctypes.c_int
@@ -373,6 +381,19 @@ class Context(object):
                                                   ctypes.c_void_p(line_ptr or 0), int(line_cap),
                                                   ctypes.c_void_p(stats_ptr or 0))
         self._check(rc)
+
+    def pileup_consensus_batch_dev(self, samples, sites, params, mode):
+        """Batch form of pileup_consensus_dev: samples = sequence of (text_ptr, nbytes, row_ptr, line_ptr, line_cap,
+        stats_ptr) tuples of device pointers (0 = none), or a ready (PileupSample * n) array.  One launch sequence per 16
+        samples; nothing is synchronised."""
+        if isinstance(samples, ctypes.Array):
+            arr = samples
+        else:
+            arr = (PileupSample * len(samples))()
+            for k, (tp, nb, rp, lp, lc, sp) in enumerate(samples):
+                arr[k] = PileupSample(tp or None, int(nb), rp or None, lp or None, int(lc), sp or None)
+        self._check(self.lib.snpgpu_pileup_consensus_batch_dev(self.handle, arr, len(arr), sites.handle,
+                                                               ctypes.byref(params), mode))
 
     # -- K2 ---------------------------------------------------------------------------------------
     def merge_sites(self, keys, sample_of):

@@ -35,11 +35,11 @@ struct DevBuf {
 struct snpgpu_ctx {
     int          device = 0;
     int          n_sms = 148;
-    int          k1_blocks[2] = {1, 1};      // resident CTAs per SM of the pileup kernel, [has_qual]
+    int          k1_blocks = 1;              // resident CTAs per SM of the pileup kernel
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t     launches = 0;
     std::string  err;
-    DevBuf k1_zero, tile_first, tile_lines, stage, over, arena, stats;   // k1_zero: status | site_cells, cleared by one memset per call
+    DevBuf k1_zero, tile_first, tile_lines, lane_lines, stage, over, arena, queue, stats;   // k1_zero: counters | per sample status, site cells: one memset per batch
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     size_t text_nbytes = 0;                   // bytes of the last text snpgpu_pileup_consensus() staged ...
     bool   text_valid = false;                // ... still there (snpgpu_pileup_vcf_records works on it)
@@ -62,7 +62,8 @@ struct snpgpu_ctx {
     cudaEvent_t lane_event = nullptr;
     std::vector<std::pair<void *, size_t>> sites_pool;   // blobs of destroyed device-built site tables, reused in stream order
     size_t arena_want = 1 << 20;
-    size_t over_want = 1 << 16;              // entries of the per-line results' overflow list (tiles of tiny lines)
+    size_t over_want = 1 << 16;              // entries of a sample's overflow list of per-line results (lanes with many tiny lines)
+    size_t queue_want = 0;                   // entries of the follow-up kernel's queue, once a batch has asked for more
     bool   timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];     // pending event pairs per kernel id
     std::vector<cudaEvent_t> spare_events;
@@ -130,8 +131,7 @@ int snpgpu_create(int device, snpgpu_ctx **out) {
     ctx->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SNPGPU_E_CUDA; }
     ctx->stream = ctx->own_stream;
-    ctx->k1_blocks[0] = std::max(1, k1_blocks_per_sm(false));
-    ctx->k1_blocks[1] = std::max(1, k1_blocks_per_sm(true));
+    ctx->k1_blocks = std::max(1, k1_blocks_per_sm());
     if (cudaGetLastError() != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return SNPGPU_E_CUDA; }
     *out = ctx;
     return SNPGPU_OK;
@@ -146,7 +146,7 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
         if (ctx->lane_stats[k]) cudaFreeHost(ctx->lane_stats[k]);
     }
     if (ctx->lane_event) cudaEventDestroy(ctx->lane_event);
-    DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->tile_lines, &ctx->stage, &ctx->over, &ctx->arena,
+    DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->tile_lines, &ctx->lane_lines, &ctx->stage, &ctx->over, &ctx->arena, &ctx->queue,
                      &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
                      &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
@@ -409,64 +409,138 @@ int snpgpu_reference_bases(snpgpu_ctx *ctx, const uint8_t *seq, size_t seq_len, 
 }
 
 // ------------------------------------------------------------------------------------------ K1
+// One launch sequence over up to K1_BATCH samples: memset of the scratch that starts as zeros, pileup kernel + follow-up
+// kernel, the two ordering kernels (per-line results wanted), finish kernel.  rec_*: the consensus-VCF pass's line list
+// (single sample only).
+static int k1_run_batch(snpgpu_ctx *ctx, const snpgpu_pileup_sample *smp, size_t n, const snpgpu_sites *sites,
+                        const snpgpu_params *params, int mode, unsigned long long *rec_off, unsigned long long *rec_count,
+                        size_t rec_cap) {
+    cudaStream_t st = ctx->stream;
+    const bool has_qual = params->min_base_qual > 0;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // ---- geometry
+    int tile0[K1_BATCH + 1], max_tiles = 0;
+    size_t total_bytes = 0, stage_tiles = 0;
+    bool want_lines = false;
+    tile0[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        const size_t nt = (smp[i].nbytes + K1_TILE - 1) / K1_TILE;
+        if (nt + (size_t)tile0[i] >= ((size_t)1 << 31)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: batch too large");
+        tile0[i + 1] = tile0[i] + (int)nt;
+        max_tiles = std::max(max_tiles, (int)nt);
+        total_bytes += smp[i].nbytes;
+        if (mode == SNPGPU_MODE_ALL && smp[i].line_out_dev) { want_lines = true; stage_tiles += nt + 1; }
+    }
+    // ---- scratch that starts as zeros: ticket + queue counters | per sample: status, lines per tile group, site cells
+    const size_t z_head = 256;
+    const size_t z_groups = want_lines ? up(((size_t)max_tiles / K1_ORDER_TILES + 2) * sizeof(unsigned long long)) : 0;
+    const size_t z_cells = up((sites->n_unique + 1) * sizeof(unsigned long long));
+    const size_t z_per = 256 + z_groups + z_cells;
+    static_assert(sizeof(PileupStatusDev) <= 256, "status block");
+    const size_t z_total = z_head + n * z_per;
+    CK(ctx->k1_zero.ensure(z_total));
+    CK(ctx->arena.ensure(ctx->arena_want));
+    const size_t q_cap = std::max<size_t>(ctx->queue_want, has_qual ? total_bytes / 8 + 65536 : total_bytes / 512 + 65536);
+    CK(ctx->queue.ensure(q_cap * 16));
+    if (want_lines) {
+        CK(ctx->tile_first.ensure(stage_tiles * sizeof(unsigned long long)));
+        CK(ctx->tile_lines.ensure(stage_tiles * sizeof(uint32_t)));
+        CK(ctx->lane_lines.ensure(stage_tiles * 32));
+        CK(ctx->stage.ensure(stage_tiles * K1_LCAP * 32 * sizeof(uint16_t)));
+        CK(ctx->over.ensure(n * ctx->over_want * sizeof(unsigned long long)));
+    }
+    CK(cudaMemsetAsync(ctx->k1_zero.p, 0, z_total, st));
+    uint8_t *zb = (uint8_t *)ctx->k1_zero.p;
+    K1Batch g;
+    memset(&g, 0, sizeof(g));
+    size_t tiles_before = 0;
+    for (size_t i = 0; i < n; i++) {
+        K1Samp &S = g.s[i];
+        uint8_t *zs = zb + z_head + i * z_per;
+        const bool lines = mode == SNPGPU_MODE_ALL && smp[i].line_out_dev;
+        S.text = (const uint8_t *)smp[i].text_dev;
+        S.nbytes = smp[i].nbytes;
+        S.tile0 = tile0[i];
+        S.n_tiles = tile0[i + 1] - tile0[i];
+        S.st = (PileupStatusDev *)zs;
+        S.group_lines = lines ? (unsigned long long *)(zs + 256) : nullptr;
+        S.site_cells = (unsigned long long *)(zs + 256 + z_groups);
+        if (lines) {
+            S.tile_first = (unsigned long long *)ctx->tile_first.p + tiles_before;
+            S.tile_lines = (uint32_t *)ctx->tile_lines.p + tiles_before;
+            S.lane_lines = (uint8_t *)ctx->lane_lines.p + tiles_before * 32;
+            S.stage = (uint16_t *)ctx->stage.p + tiles_before * K1_LCAP * 32;
+            S.over = (unsigned long long *)ctx->over.p + i * ctx->over_want;
+            S.line_out = smp[i].line_out_dev;
+            S.line_out_cap = smp[i].line_out_cap;
+            tiles_before += (size_t)S.n_tiles + 1;
+        }
+        S.rec_off = rec_off; S.rec_count = rec_count; S.rec_cap = rec_cap;
+        S.row_out = smp[i].row_out_dev;
+        S.stats_out = smp[i].stats_dev;
+    }
+    g.n_samples = (int)n;
+    g.total_tiles = tile0[n];
+    g.mode = mode;
+    g.has_qual = has_qual ? 1 : 0;
+    g.all_rest = (has_qual || rec_off) ? 1 : 0;
+    g.one = 1u;
+    g.next_tile = (unsigned int *)zb;
+    g.queue_count = (unsigned long long *)(zb + 8);
+    g.queue = (unsigned long long *)ctx->queue.p;
+    g.queue_cap = q_cap;
+    g.over_cap = want_lines ? ctx->over_want : 0;
+    g.arena = (uint8_t *)ctx->arena.p;
+    g.arena_cap = ctx->arena.cap;
+    g.snp_unique = sites->snp_unique;
+    g.n_snp = sites->n_snp;
+    g.sites = sites->table;
+    memcpy(&g.p, params, sizeof(CallParams));
+    {
+        TimedLaunch t(ctx, SNPGPU_KERNEL_PILEUP);
+        ctx->launches += (uint64_t)k1_launch(st, g, ctx->n_sms * ctx->k1_blocks, ctx->n_sms);
+    }
+    ctx->launches += (uint64_t)k1_launch_finish(st, g, max_tiles, want_lines);
+    CK(cudaGetLastError());
+    return SNPGPU_OK;
+}
+
+static int k1_check(snpgpu_ctx *ctx, const snpgpu_pileup_sample *smp, size_t n, const snpgpu_sites *sites,
+                    const snpgpu_params *params, int mode) {
+    if (!ctx || !sites || !params || (n && !smp)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null argument");
+    if (mode != SNPGPU_MODE_SITES && mode != SNPGPU_MODE_ALL) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: bad mode");
+    for (size_t i = 0; i < n; i++) {
+        if (smp[i].nbytes && !smp[i].text_dev) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null text");
+        if (((uintptr_t)smp[i].text_dev & 15u) != 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text must be 16-byte aligned");
+        if (sites->n_snp && !smp[i].row_out_dev) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: row_out is null");
+        if (smp[i].nbytes >= ((size_t)1 << 38)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text of 256 GiB or more");
+    }
+    return SNPGPU_OK;
+}
+
+int snpgpu_pileup_consensus_batch_dev(snpgpu_ctx *ctx, const snpgpu_pileup_sample *samples, size_t n_samples,
+                                      const snpgpu_sites *sites, const snpgpu_params *params, int mode) {
+    int rc = k1_check(ctx, samples, n_samples, sites, params, mode);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n_samples; i += K1_BATCH) {
+        rc = k1_run_batch(ctx, samples + i, std::min<size_t>(K1_BATCH, n_samples - i), sites, params, mode, nullptr, nullptr, 0);
+        if (rc) return rc;
+    }
+    return SNPGPU_OK;
+}
+
 static int k1_run(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
                   const snpgpu_params *params, int mode, uint8_t *row_out_dev, uint16_t *line_out_dev,
                   size_t line_out_cap, snpgpu_pileup_stats *stats_dev, unsigned long long *rec_off,
                   unsigned long long *rec_count, size_t rec_cap) {
-    if (!ctx || !sites || !params || (nbytes && !text_dev)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: null argument");
-    if (mode != SNPGPU_MODE_SITES && mode != SNPGPU_MODE_ALL) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: bad mode");
-    if (((uintptr_t)text_dev & 15u) != 0) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text must be 16-byte aligned");
-    if (sites->n_snp && !row_out_dev) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: row_out is null");
-    if (nbytes >= ((size_t)1 << 38)) return fail(ctx, SNPGPU_E_ARG, "pileup_consensus: text of 256 GiB or more");
+    snpgpu_pileup_sample s;
+    s.text_dev = text_dev; s.nbytes = nbytes; s.row_out_dev = row_out_dev;
+    s.line_out_dev = mode == SNPGPU_MODE_ALL ? line_out_dev : nullptr; s.line_out_cap = line_out_cap; s.stats_dev = stats_dev;
+    int rc = k1_check(ctx, &s, 1, sites, params, mode);
+    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const int n_tiles = (int)((nbytes + K1_TILE - 1) / K1_TILE);
-    const bool want_lines = mode == SNPGPU_MODE_ALL && line_out_dev != nullptr;
-    // per-call scratch that starts as zeros, in one allocation: status | site_cells
-    const size_t z_status = 0, z_groups = 256;                // status | lines per tile group | site_cells
-    const size_t z_cells = z_groups + (want_lines ? (((size_t)n_tiles / K1_ORDER_TILES + 2) * sizeof(unsigned long long) + 255) & ~(size_t)255 : 0);
-    const size_t z_total = z_cells + (sites->n_unique + 1) * sizeof(unsigned long long);
-    static_assert(sizeof(PileupStatusDev) <= 64, "status block (the tuning build's counters follow it)");
-    CK(ctx->k1_zero.ensure(z_total));
-    CK(ctx->arena.ensure(ctx->arena_want));
-    if (want_lines) {                                         // per-line results: staged per tile, ordered afterwards
-        CK(ctx->tile_first.ensure(((size_t)n_tiles + 1) * sizeof(unsigned long long)));
-        CK(ctx->tile_lines.ensure(((size_t)n_tiles + 1) * sizeof(uint32_t)));
-        CK(ctx->stage.ensure(((size_t)n_tiles + 1) * K1_STAGE_CAP * sizeof(uint16_t)));
-        CK(ctx->over.ensure(ctx->over_want * sizeof(unsigned long long)));
-    }
-    CK(cudaMemsetAsync(ctx->k1_zero.p, 0, z_total, st));
-    uint8_t *zb = (uint8_t *)ctx->k1_zero.p;
-    PileupArgs a;
-    a.text = (const uint8_t *)text_dev;
-    a.nbytes = nbytes;
-    a.sites = sites->table;
-    memcpy(&a.p, params, sizeof(CallParams));
-    a.mode = mode;
-    a.n_tiles = n_tiles;
-    a.site_cells = (unsigned long long *)(zb + z_cells);
-    a.line_out = want_lines ? line_out_dev : nullptr;
-    a.line_out_cap = want_lines ? (unsigned long long)line_out_cap : 0ull;
-    a.tile_lines = want_lines ? (uint32_t *)ctx->tile_lines.p : nullptr;
-    a.group_lines = want_lines ? (unsigned long long *)(zb + z_groups) : nullptr;
-    a.stage = want_lines ? (uint16_t *)ctx->stage.p : nullptr;
-    a.over = want_lines ? (unsigned long long *)ctx->over.p : nullptr;
-    a.over_cap = want_lines ? (unsigned long long)ctx->over_want : 0ull;
-    a.tile_first = want_lines ? (unsigned long long *)ctx->tile_first.p : nullptr;
-    a.st = (PileupStatusDev *)(zb + z_status);
-    a.rec_off = rec_off; a.rec_count = rec_count; a.rec_cap = rec_cap;
-    a.arena = (uint8_t *)ctx->arena.p;
-    a.arena_cap = ctx->arena.cap;
-    const int bps = ctx->k1_blocks[params->min_base_qual > 0 ? 1 : 0];
-    {
-        TimedLaunch t(ctx, SNPGPU_KERNEL_PILEUP);
-        ctx->launches += (uint64_t)k1_launch(st, a, ctx->n_sms * bps);
-    }
-    ctx->launches += (uint64_t)k1_launch_order(st, a);
-    ctx->launches += (uint64_t)k1_launch_finish(st, a.site_cells, sites->snp_unique, sites->n_snp, row_out_dev, a.st, a.over_cap,
-                                                stats_dev);
-    CK(cudaGetLastError());
-    return SNPGPU_OK;
+    return k1_run_batch(ctx, &s, 1, sites, params, mode, rec_off, rec_count, rec_cap);
 }
 
 int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, const snpgpu_sites *sites,
@@ -474,6 +548,13 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
                                 size_t line_out_cap, snpgpu_pileup_stats *stats_dev) {
     return k1_run(ctx, text_dev, nbytes, sites, params, mode, row_out_dev, line_out_dev, line_out_cap, stats_dev, nullptr,
                   nullptr, 0);
+}
+
+// what a batch that came back with SNPGPU_E_NOMEM asked for (k1_finish_kernel)
+static void k1_grow(snpgpu_ctx *ctx, const snpgpu_pileup_stats &hs) {
+    if (hs.reserved < 0) { ctx->queue_want = (size_t)hs.error_offset + 65536; return; }
+    if (hs.error_offset) ctx->arena_want = (size_t)hs.error_offset + (1 << 20);
+    if (hs.reserved > 0) ctx->over_want = ((size_t)hs.reserved << 10) + (1 << 16);
 }
 
 int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, const snpgpu_sites *sites,
@@ -486,7 +567,7 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
     bool normalized = false, skip_copy = false;
     ctx->text_valid = false;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 4; attempt++) {
         CK(ctx->text.ensure(nbytes + 64));
         CK(ctx->row.ensure(sites->n_snp + 16));
         CK(ctx->stats.ensure(sizeof(snpgpu_pileup_stats)));
@@ -507,11 +588,12 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
             skip_copy = true;
             continue;
         }
-        if (hs.error_code == SNPGPU_E_NOMEM && attempt == 0) {    // the splice scratch or the overflow list was too small: grow, redo
-            if (hs.error_offset) ctx->arena_want = (size_t)hs.error_offset + (1 << 20);
-            if (hs.reserved > 0) ctx->over_want = ((size_t)hs.reserved << 10) + (1 << 16);
+        if (hs.error_code == SNPGPU_E_NOMEM && attempt < 3) {     // the follow-up queue, the splice scratch or the overflow list
+            k1_grow(ctx, hs);                                     // was too small: grow, redo
+            skip_copy = true;
             continue;
         }
+        if (hs.error_code == SNPGPU_E_NOMEM) return fail(ctx, SNPGPU_E_NOMEM, "pileup_consensus: device scratch kept growing");
         if (want_lines && hs.error_code == 0) {
             size_t n = (size_t)std::min<uint64_t>(hs.n_lines, line_out_cap);
             if (n) CK(cudaMemcpy(line_out, ctx->lines.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));

@@ -23,58 +23,93 @@ struct PileupStatusDev {
     unsigned long long over_used;     // entries claimed in the per-line results' overflow list
 };
 
-// Tile geometry of the pileup kernel: every warp is its own pipeline.
-#ifndef K1_CFG_CHUNKS          // (tuning builds override these four on the nvcc command line)
-#define K1_CFG_CHUNKS 21
-#define K1_CFG_CTAS 4
-#define K1_CFG_LHCAP 10
-#define K1_CFG_QCAP 64
+// ---- geometry of the pileup kernel (k1_pileup.cu): every warp is its own pipeline --------------
+#ifndef K1_CFG_WARPS           // (tuning builds override these on the nvcc command line)
+#define K1_CFG_WARPS 20
+#define K1_CFG_LANE_BYTES 336
+#define K1_CFG_LOOK 208
 #endif
-constexpr int K1_LANE_CHUNKS = K1_CFG_CHUNKS;             // 16-byte chunks one lane scans for newlines ...
-constexpr int K1_LANE_BYTES  = 16 * K1_LANE_CHUNKS;   // ... an odd number: stride = 4 mod 8 words, quarter warps hit disjoint banks
-constexpr int K1_TILE     = 32 * K1_LANE_BYTES;       // bytes of text whose line starts one tile owns
-#ifndef K1_CFG_LOOK
-#define K1_CFG_LOOK 896
-#define K1_CFG_WCAP 192
-#endif
-constexpr int K1_LOOK     = K1_CFG_LOOK;              // extra bytes staged so that the last owned line is complete
-constexpr int K1_PAD      = 32;                // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_WARPS    = 4;                 // independent warps per CTA
-constexpr int K1_THREADS  = 32 * K1_WARPS;
-constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;              // 16 warps x 13.6 KiB of shared memory per SM, 128 registers per thread
-constexpr int K1_WCAP     = K1_CFG_WCAP;               // line starts a warp lists per pass (more -> another pass)
-constexpr int K1_LHCAP    = K1_CFG_LHCAP;                // line starts one lane lists per tile (more -> byte-wise path)
-constexpr int K1_ORDER_TILES = 512;            // tiles per group of the ordering pass (k1_tile_prefix_kernel)
-constexpr int K1_STAGE_CAP = 320;              // per-line results a tile keeps in its row of the staging array (a tile of the
-                                               // scan's own path owns at most 32 (K1_LHCAP - 1) + 1 lines; more -> overflow list)
-constexpr int K1_NAMEW    = 16;                // words of the expected contig's name a warp keeps in shared memory
-constexpr int K1_DRAIN_AT = 24;                // queued lines that trigger a drain between two tiles (32: also inside a tile)
-constexpr int K1_QCAP     = K1_CFG_QCAP;                // per-warp queue slots (drained whenever 32 are filled)
+#define K1_CFG_CTAS 1
+constexpr int K1_WARPS       = K1_CFG_WARPS;         // independent warps per CTA; one CTA per SM (it shares the filter tables)
+constexpr int K1_THREADS     = 32 * K1_WARPS;
+constexpr int K1_CTAS_PER_SM = K1_CFG_CTAS;
+constexpr int K1_LANE_BYTES  = K1_CFG_LANE_BYTES;    // bytes of a tile one lane owns: lines whose preceding '\n' lies there are its
+constexpr int K1_TILE        = 32 * K1_LANE_BYTES;   // bytes of text whose line starts one tile (= one warp-step) owns
+constexpr int K1_LOOK        = K1_CFG_LOOK;          // extra bytes staged so that the last owned line is complete
+constexpr int K1_WIN         = K1_TILE + K1_LOOK;
+constexpr int K1_PAD         = 32;                   // '\n' sentinels after the staged bytes (word over-reads land here)
+constexpr int K1_LCAP        = 8;                    // per-line results a lane keeps in the staging array per tile (more -> overflow list)
+constexpr int K1_ORDER_TILES = 512;                  // tiles per group of the ordering pass (k1_tile_prefix_kernel)
+constexpr int K1_NAMEW       = 16;                   // words of the expected contig's name a warp keeps in shared memory
+constexpr int K1_BATCH       = 16;                   // samples one launch of the pileup kernel takes (the descriptors are kernel parameters)
+static_assert(K1_LANE_BYTES % 16 == 0 && K1_LANE_BYTES <= 1008 && K1_WIN % 16 == 0, "tile geometry");
 
+// What the second / third parser tiers (line_fast.cuh, line_general.cuh) see of one sample: built per line by the
+// follow-up kernel from the batch descriptor below.
 struct PileupArgs {
     const uint8_t      *text;          // 16-byte aligned
     unsigned long long  nbytes;
     SiteTable           sites;
     CallParams          p;
     int                 mode;          // SNPGPU_MODE_SITES / SNPGPU_MODE_ALL
-    int                 n_tiles;
     unsigned long long *site_cells;    // n_unique, zero-initialised: ((line offset + 1) << 8) | cell  (atomicMax:
                                        // the last line in file order wins, like the dict of call_consensus.py:169)
-    uint16_t           *line_out;      // null, or one uint16 per line in file order: cell | fail << 8
-    unsigned long long  line_out_cap;
-    uint32_t           *tile_lines;    // [n_tiles]: lines each tile owns (written by the tile's warp, when line_out)
-    unsigned long long *group_lines;   // zero-initialised: lines per group of K1_ORDER_TILES tiles (atomic adds)
-    uint16_t           *stage;         // [n_tiles][K1_STAGE_CAP]: per-line results, tile by tile (when line_out)
-    unsigned long long *over;          // overflow list of (tile << 32 | index << 16 | result) for tiles above K1_STAGE_CAP ...
+    uint16_t           *stage;         // null, or [n_tiles][K1_LCAP][32]: per-line results, slot k of lane L of a tile
+    unsigned long long *over;          // overflow list of (tile * 32 + lane) << 32 | k << 16 | result for lanes above K1_LCAP lines ...
     unsigned long long  over_cap;      // ... its capacity (PileupStatusDev::over_used counts the claims)
-    unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (k1_tile_prefix_kernel)
     unsigned long long *rec_off;       // null, or: file offset of every parsed line is appended here (any order) ...
     unsigned long long *rec_count;     // ... through this counter (the consensus-VCF pass, k5_vcf.cu)
     unsigned long long  rec_cap;
     PileupStatusDev    *st;
     uint8_t            *arena;
     unsigned long long  arena_cap;
+    PileupStatusDev    *arena_st;      // whose arena_used / arena_overflow count the claims (the arena is shared by a batch)
 };
+
+// One sample of a batch, as the kernels see it
+struct K1Samp {
+    const uint8_t      *text;          // 16-byte aligned
+    unsigned long long  nbytes;
+    int                 tile0;         // first ticket of the batch that belongs to this sample
+    int                 n_tiles;
+    unsigned long long *site_cells;    // n_unique + 1, zero-initialised
+    PileupStatusDev    *st;            // zero-initialised
+    uint16_t           *stage;         // null (no per-line results wanted), or [n_tiles][K1_LCAP][32]
+    uint8_t            *lane_lines;    // [n_tiles][32]: lines each lane owns
+    uint32_t           *tile_lines;    // [n_tiles]
+    unsigned long long *group_lines;   // zero-initialised: lines per group of K1_ORDER_TILES tiles
+    unsigned long long *tile_first;    // [n_tiles]: file-order index of a tile's first line (k1_tile_prefix_kernel)
+    unsigned long long *over;          // overflow list of this sample, over_cap entries
+    uint16_t           *line_out;      // one uint16 per line in file order: cell | fail << 8
+    unsigned long long  line_out_cap;
+    unsigned long long *rec_off;       // see PileupArgs
+    unsigned long long *rec_count;
+    unsigned long long  rec_cap;
+    uint8_t            *row_out;       // n_snp bytes, snplist order
+    snpgpu_pileup_stats *stats_out;    // nullable
+};
+
+struct K1Batch {
+    K1Samp              s[K1_BATCH];   // tile0 ascending
+    int                 n_samples;
+    int                 total_tiles;
+    int                 mode;
+    int                 has_qual;      // min_base_qual > 0: line_fast.cuh pairs every base with its quality
+    int                 all_rest;      // every line that is parsed goes to the follow-up kernel (has_qual, or the VCF pass's line list is wanted)
+    uint32_t            one;           // 1: the multiplier of line_quick3.cuh's IMAD adds (a value the compiler cannot fold)
+    unsigned int       *next_tile;     // zero-initialised ticket counter
+    unsigned long long *queue;         // lines for the follow-up kernel: 2 words per entry (k1_entry, sample | flags << 32)
+    unsigned long long  queue_cap;     // ... entries
+    unsigned long long *queue_count;   // zero-initialised; may run past queue_cap (reported as SNPGPU_E_NOMEM)
+    unsigned long long  over_cap;
+    uint8_t            *arena;         // splice scratch of line_general.cuh, shared by the batch (claimed through s[0].st)
+    unsigned long long  arena_cap;
+    const int32_t      *snp_unique;    // n_snp: unique-site index of snplist entry k
+    unsigned long long  n_snp;
+    SiteTable           sites;
+    CallParams          p;
+};
+static_assert(sizeof(K1Batch) <= 4000, "the batch descriptor travels as a kernel parameter");
 
 // ---- PTX: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

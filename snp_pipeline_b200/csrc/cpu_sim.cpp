@@ -10,12 +10,25 @@
 #include <vector>
 #include "line_fast.cuh"
 #include "line_quick.cuh"
+#include "line_quick3.cuh"
 #include "line_general.cuh"
 #include "sites_host.h"
 
 using namespace snpgpu;
 
+static int g_variant = 1;      // 0: line_quick.cuh (the round-1 first tier, kept as a second opinion), 1: line_quick3.cuh (k1_pileup.cu)
+
+struct HostWin {                // line_quick3.cuh's memory policy over a plain array: window words, then the name rows
+    const uint32_t *p;
+    const uint16_t *tab;
+    uint32_t ld(uint32_t k) const { return p[k]; }
+    uint32_t tab16(uint32_t k) const { return tab[k]; }
+    void ld4(uint32_t k, uint32_t *w) const { w[0] = p[k]; w[1] = p[k + 1]; w[2] = p[k + 2]; w[3] = p[k + 3]; }
+};
+
 extern "C" {
+
+void cpusim_set_variant(int v) { g_variant = v; }
 
 // counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code,
 // [5] = lines decided by the first-tier parser
@@ -31,7 +44,13 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
     SiteTable t = h.view();
     std::vector<uint64_t> cells(h.n_unique + 1, 0);
     // staging copy: 4-byte aligned, '\n' sentinels behind the text (what the kernel's shared-memory window looks like)
-    std::vector<uint32_t> store((nbytes + 64) / 4 + 4, 0x0a0a0a0au);
+    std::vector<uint32_t> store((nbytes + 64) / 4 + 8 + Q3_ROWS_WORDS, 0x0a0a0a0au);   // ... followed by the name rows
+    const uint32_t rows_w = (uint32_t)(((nbytes + 64) / 4 + 7) & ~(size_t)3);
+    uint32_t *rows = store.data() + rows_w;
+    Q3Contig cc3;
+    int cc3_cid = -2;
+    std::vector<uint16_t> tab(2 * Q3_TABN);
+    for (uint32_t k = 0; k < 2 * Q3_TABN; k++) tab[k] = (uint16_t)q3_tab_entry(k, *p);
     uint8_t *buf = reinterpret_cast<uint8_t *>(store.data());
     memcpy(buf, text, nbytes);
     memset(buf + nbytes, '\n', 48);
@@ -57,10 +76,54 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         const size_t line_idx = n_lines++;
         int st = ST_FALLBACK;
         FastLine fl;
-        if (!force_general && !high && p->min_base_qual <= 0) {       // first tier (line_quick.cuh)
+        if (!force_general && (!high || g_variant == 1) && p->min_base_qual <= 0) {   // first tier (k1_stream.cu has no tile-wide byte check)
             QuickLine q;
             if (cc.cid != hint) contig_cache_load(t, hint, cc_name, cc_mask, 16, &cc);    // the kernel reloads after a drain
-            st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
+            if (g_variant == 0) {
+                st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
+            } else {                                                     // the steps of k1_pileup.cu's lane loop
+                if (cc3_cid != hint) {                                   // (the kernel follows the tile's first line)
+                    const uint32_t L = (uint32_t)(t.name_off[hint + 1] - t.name_off[hint]) + 1u;
+                    auto name_at = [&](uint32_t idx) { return t.names[t.name_off[hint] + idx]; };
+                    const uint32_t nw = ((L + 6u) >> 2) < 3u ? 3u : (L + 6u) >> 2;
+                    for (uint32_t a = 0; a < 4u; a++) {
+                        uint32_t dummy;
+                        for (uint32_t j = 0; j < Q3_NAMEW; j++) q3_row_word(name_at, L, a, j, &rows[a * Q3_NAMEW + j], &dummy);
+                        for (uint32_t j = 0; j < 8u; j++) q3_row_word(name_at, L, a, j, &dummy, &rows[Q3_MASK8_W + 8u * a + j]);
+                        q3_row_word(name_at, L, a, 0u, &dummy, &rows[Q3_MASKC_W + 4u * a]);
+                        q3_row_word(name_at, L, a, nw - 2u, &dummy, &rows[Q3_MASKC_W + 4u * a + 1u]);
+                        q3_row_word(name_at, L, a, nw - 1u, &dummy, &rows[Q3_MASKC_W + 4u * a + 2u]);
+                    }
+                    q3_contig_set(&cc3, rows_w, L, hint, t.max_pos[hint], t.bit_base[hint]);
+                    cc3_cid = hint;
+                }
+                const HostWin m{store.data(), tab.data()};
+                uint32_t odd = 0;
+                const uint32_t nl = q3_find_nl(m, (uint32_t)s, 1u, &odd);
+                if (nl != e) { counters[3] = s; counters[4] = 97; break; }          // harness self-check: the line end
+                bool seen_odd = false;
+                for (size_t x = s; x < e; x++) seen_odd |= (buf[x] >= 0x0b && buf[x] <= 0x0d);
+                if (seen_odd && !odd) { counters[3] = s; counters[4] = 96; break; }  // ... and the odd-byte flag
+                Q3Line q3;
+                st = ST_DETAIL;
+                if (q3_key(m, (uint32_t)s, (uint32_t)nbytes, cc3, 1u, &q3)) {
+                    const bool known = (int32_t)q3.pos <= cc3.max_pos;
+                    const uint32_t widx = cc3.word_base + (q3.pos >> 5), bb = q3.pos & 31u;
+                    if (!all_positions && !(known && ((t.bits[widx] >> bb) & 1u))) st = ST_SKIP;
+                    else {
+                        SiteWord sw{0u, 0u, 0u, 0u};
+                        if (known) sw = t.words[widx];
+                        st = q3_rest(m, q3.after, (uint32_t)nbytes, *p, 1u, &q3);
+                        if (st == ST_OK) {
+                            uint32_t fl3;
+                            q3_site(sw, bb, &q.site, &fl3);
+                            q.flags = (uint8_t)fl3; q.end = q3.end; q.base = q3.base; q.fail = q3.fail;
+                        }
+                    }
+                }
+                if (st == ST_SKIP && odd) st = ST_DETAIL;               // (the kernel declines odd lines it would skip)
+            }
+            if (high && (st == ST_OK || st == ST_SKIP)) { counters[3] = s; counters[4] = 95; break; }   // must decline bytes >= 0x80
             if (st == ST_OK) {
                 if (q.end != e) { counters[3] = s; counters[4] = 99; break; }   // harness self-check: the line end
                 if (q.flags != (q.site >= 0 ? h.flags[q.site] : 0)) { counters[3] = s; counters[4] = 98; break; }   // ... and the site's flags
@@ -68,6 +131,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
                 n_quick++;
             }
         }
+        if (high) st = ST_FALLBACK;
         if (!force_general && !high && (st == ST_DETAIL || p->min_base_qual > 0)) {
             if (p->min_base_qual > 0) st = fast_line<true>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);
             else st = fast_line<false>(buf, (uint32_t)s, (uint32_t)e, t, hint, *p, all_positions != 0, &fl);

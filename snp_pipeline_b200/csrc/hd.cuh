@@ -41,11 +41,12 @@ SNP_HD unsigned low8(unsigned c) { return (c - 'A' < 26u) ? c + 32u : c; }
 SNP_HD bool py_space(unsigned c) { return c == 0x20u || (c - 9u) < 5u || (c - 0x1cu) < 4u; }
 SNP_HD bool is_digit(unsigned c) { return (c - '0') < 10u; }
 
-// 32-bit funnel shift right by sh in {0, 8, 16, 24} bits: the little-endian word that starts sh/8 bytes into lo
+// 32-bit funnel shift right by (sh & 31) in {0, 8, 16, 24} bits: the little-endian word that starts sh/8 bytes into lo
 SNP_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(lo, hi, sh);
 #else
+    sh &= 31u;
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }

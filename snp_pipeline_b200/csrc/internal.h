@@ -6,13 +6,10 @@ namespace snpgpu {
 
 // k1_pileup.cu
 size_t k1_smem_bytes();
-int    k1_blocks_per_sm(bool has_qual);
-// enqueue the pileup kernel over `a`; returns the number of kernels launched
-int    k1_launch(cudaStream_t stream, const PileupArgs &a, int grid_blocks);
-int    k1_launch_order(cudaStream_t stream, const PileupArgs &a);
-int    k1_launch_finish(cudaStream_t stream, const unsigned long long *site_cells, const int32_t *snp_unique,
-                        size_t n_snp, uint8_t *row_out_dev, const PileupStatusDev *st, unsigned long long over_cap,
-                        snpgpu_pileup_stats *stats_dev);
+int    k1_blocks_per_sm();
+// the pileup kernel + its follow-up kernel over a batch; returns the number of kernels launched
+int    k1_launch(cudaStream_t stream, const K1Batch &g, int grid_blocks, int n_sms);
+int    k1_launch_finish(cudaStream_t stream, const K1Batch &g, int max_tiles, bool want_lines);
 int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
 
 // k5_vcf.cu

@@ -1,0 +1,339 @@
+// line_quick3.cuh -- the first-tier parser of the pileup kernel (k1_pileup.cu): one lane walks one line.
+//
+// It decides the lines whose call does not depend on WHICH other symbols a read carries -- after pileup.py:276-325 has
+// stripped "^x" and "$", the '.' / ',' outnumber every other surviving byte together and none of those is the reference
+// letter written out, so the reference base is the strict winner of pileup.py:260-266 and the caller (pileup.py:550-588)
+// only needs
+//     good_depth = surviving bytes,  consensus depth = '.' + ',',  forward = '.',  reverse = ','.
+// Every byte of the line is validated on the way (contig name, separators, digits, a printable quality string exactly as
+// long as the stripped bases -- the zip() of pileup.py:248); anything else is declined with ST_DETAIL and no side effects:
+// an indel token, "^^", a trailing '^', depth 0, another contig, "\r\n", a byte >= 0x80 ...  Declined lines go to the
+// follow-up kernel (line_fast.cuh -> line_general.cuh).
+//
+// Written for the integer pipes of sm_100 (profiles/micro/pipes.cu): LOP3 / SHF / PRMT issue on the ALU pipe, IMAD and
+// IDP.4A on the FMA pipe, each at one warp-instruction per two cycles per scheduler -- so the SWAR range tests add their
+// constants with IMAD (multiplier `one`, a kernel parameter the compiler cannot fold) and count flags with IDP.4A, which
+// leaves the ALU pipe the logic only.  FLO / POPC (quarter rate) stay out of the loops.
+//
+// Memory: the parser reads the staged text through a policy object M with  uint32_t ld(uint32_t word)  -- word `word` of
+// the warp's slice of shared memory (device) or of a plain array (tests/cpu_sim): aligned 32-bit loads only, 32-bit
+// addressing, and the compiler always knows the address space.  Preconditions: '\n' sentinels in bytes
+// [limit, limit + QUICK_PAD) of the window.  Any byte values are safe: every word that takes part in a SWAR test is OR-ed
+// into a guard, and a byte >= 0x80 declines the line.
+#pragma once
+#include "line_quick.cuh"
+
+namespace snpgpu {
+
+constexpr uint32_t Q3_NAMEW = 20;      // words per alignment row of the cached contig name (names up to 63 bytes; rows 16-byte aligned)
+constexpr uint32_t Q3_MASK8_W = 4u * Q3_NAMEW;             // word offset of the [4][8] masks of the first eight words
+constexpr uint32_t Q3_MASKC_W = Q3_MASK8_W + 32u;           // ... of the [4][4] masks of words 0, nw - 2, nw - 1 (longer names)
+constexpr uint32_t Q3_ROWS_WORDS = Q3_MASKC_W + 16u;
+
+// The contig a warp currently expects.  rows: [4][Q3_NAMEW] words of name + '\t' shifted right by a = 0..3 bytes (what
+// the aligned words of a line that starts at byte a of a word look like); then [4][8] masks of the bytes that count in the
+// first eight words (names of up to 25 bytes are compared as eight masked words, no loop); then [4][4] masks of the words
+// that need one when the name is longer: word 0, word nw - 2, word nw - 1 (the words between them count whole).
+struct Q3Contig {
+    uint32_t rows_w;       // word index of the rows in the warp's slice
+    uint32_t len1;         // name length + 1 (the tab); 0: nothing cached, every line is declined
+    uint32_t nw;           // words compared per line (warp-uniform): max(3, (len1 + 6) >> 2)
+    int32_t  cid;          // index in the site table, -1: a name the table does not hold
+    int32_t  max_pos;      // largest site position on the contig, -1 when it holds none
+    uint32_t word_base;    // bit_base >> 5: first word of the contig in the site bitmap
+};
+
+// word j of alignment row a (and its mask) of a name whose bytes name_at(0 .. L-2) are followed by a tab
+template <class F>
+SNP_HD void q3_row_word(const F &name_at, uint32_t L, uint32_t a, uint32_t j, uint32_t *w, uint32_t *mk) {
+    uint32_t v = 0, m = 0;
+    for (uint32_t b = 0; b < 4u; b++) {
+        const uint32_t p = 4u * j + b;
+        if (p >= a && p - a < L) {
+            const uint32_t c = p - a + 1u < L ? (uint32_t)name_at(p - a) : (uint32_t)'\t';
+            v |= c << (8u * b);
+            m |= 0xffu << (8u * b);
+        }
+    }
+    *w = v; *mk = m;
+}
+
+SNP_HD void q3_contig_set(Q3Contig *cc, uint32_t rows_w, uint32_t L, int32_t cid, int64_t max_pos, int64_t bit_base) {
+    cc->rows_w = rows_w; cc->len1 = L; cc->cid = cid;
+    const uint32_t nw = (L + 6u) >> 2;
+    cc->nw = nw < 3u ? 3u : nw;
+    cc->max_pos = (int32_t)(max_pos > 0x7fffffff ? 0x7fffffff : max_pos);
+    cc->word_base = (uint32_t)(bit_base >> 5);
+    if (L == 0u || 4u * cc->nw > 4u * Q3_NAMEW) { cc->len1 = 0; cc->max_pos = -1; }
+}
+
+struct Q3Line {
+    uint32_t end;          // offset of the line terminator in the window
+    uint32_t pos;          // column 2
+    uint32_t after;        // offset of the byte behind the tab that ends column 2 (valid when the key columns were taken)
+    uint8_t  base;         // consensus character before the '-' substitutions of call_consensus.py:169-176
+    uint8_t  fail;         // FAIL_* mask (without FAIL_REGION)
+};
+
+// ---- the filters of pileup.py:556-584 as two threshold tables (built once per launch from the very same IEEE double
+//      products): fail VarFreq <-> cons < tf[good];  fail StrBias <-> min(fwd, rev) < tb[cons].  Indices below Q3_TABN.
+constexpr uint32_t Q3_TABN = 512;
+// smallest integer c >= 0 with !((double)c < x), capped at 65535 (x = good * min_cons_freq or cons * min_cons_strand_bias)
+SNP_HD uint32_t q3_threshold(double x) {
+    if (!(x > 0.0)) return 0u;                            // (also NaN: every comparison with it is false)
+    if (x > 65535.0) return 65535u;
+    uint32_t c = (uint32_t)x;                             // floor
+    while ((double)c < x) c++;
+    return c;
+}
+SNP_HD uint32_t q3_tab_entry(uint32_t idx, const CallParams &p) {     // entry idx of [tf | tb]
+    return idx < Q3_TABN ? q3_threshold((double)idx * p.min_cons_freq) : q3_threshold((double)(idx - Q3_TABN) * p.min_cons_strand_bias);
+}
+template <class M>
+SNP_HD uint8_t q3_filter(const M &m, uint32_t good, uint32_t cons, uint32_t fwd, uint32_t rev, const CallParams &p) {
+    if (good >= Q3_TABN) return filter_mask(good, cons, fwd, rev, p);
+    uint32_t f = 0;
+    if (cons < m.tab16(good)) f |= FAIL_VARFREQ;
+    if ((int32_t)cons < p.min_cons_depth) f |= FAIL_DEPTH;
+    const uint32_t lo = fwd < rev ? fwd : rev;
+    if ((int32_t)lo < p.min_cons_strand_depth) f |= FAIL_STRDPTH;
+    if (lo < m.tab16(Q3_TABN + cons)) f |= FAIL_STRBIAS;
+    return (uint8_t)f;
+}
+
+// the SWAR adds, on the FMA pipe: one == 1 at run time
+#define Q3_ADD(C, w)  (one * (uint32_t)(C) + (w))                       /* w + C          */
+#define Q3_NADD(C, w) (one * (0u - (uint32_t)(C) - 1u) - (w))          /* ~(w + C)       */
+
+// ---- columns 1-2: the cached contig's name + tab, 1..8 digits + tab.  false: not for this tier. ----------------------
+template <class M>
+SNP_HD bool q3_name(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc) {
+    if (cc.len1 == 0u || s + cc.len1 + 24u > limit + QUICK_PAD) return false;
+    const uint32_t a = s & 3u, k0 = s >> 2;
+    const uint32_t r = cc.rows_w + a * Q3_NAMEW;
+    uint32_t diff;
+    if (cc.nw <= 8u) {                                  // (warp-uniform) eight masked words, all loads up front
+        uint32_t n[8], mk[8], t[8];
+        m.ld4(r, n); m.ld4(r + 4u, n + 4);
+        m.ld4(cc.rows_w + Q3_MASK8_W + 8u * a, mk); m.ld4(cc.rows_w + Q3_MASK8_W + 8u * a + 4u, mk + 4);
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j++) t[j] = m.ld(k0 + j);
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j++) t[j] = (t[j] ^ n[j]) & mk[j];
+        diff = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
+    } else {
+        const uint32_t q = cc.rows_w + Q3_MASKC_W + 4u * a, nw = cc.nw;
+        diff = (m.ld(k0) ^ m.ld(r)) & m.ld(q);
+        for (uint32_t j = 1u; j + 2u < nw; j++) diff |= m.ld(k0 + j) ^ m.ld(r + j);
+        diff |= (m.ld(k0 + nw - 2u) ^ m.ld(r + nw - 2u)) & m.ld(q + 1u);
+        diff |= (m.ld(k0 + nw - 1u) ^ m.ld(r + nw - 1u)) & m.ld(q + 2u);
+    }
+    return diff == 0u;
+}
+
+template <class M>
+SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, uint32_t one, Q3Line *out) {
+    const uint32_t H = 0x80808080u;
+    out->after = s; out->pos = 0u;
+    if (!q3_name(m, s, limit, cc)) return false;
+    // 1..8 digits + tab behind the name, as the 8 bytes at offset i (nine digits or more: next tier)
+    const uint32_t i = s + cc.len1, k = i >> 2, sh = i << 3;
+    const uint32_t a = m.ld(k), b = m.ld(k + 1u), c = m.ld(k + 2u);
+    const uint32_t rl = funnel_r(a, b, sh), rh = funnel_r(b, c, sh);
+    const uint32_t xl = rl ^ 0x30303030u, xh = rh ^ 0x30303030u;                      // digits -> 0..9
+    const uint32_t ndl = Q3_ADD(0x76767676u, xl) & H, ndh = Q3_ADD(0x76767676u, xh) & H;   // bit 7: not a digit
+    const bool in_lo = ndl != 0u, eight = (ndl | ndh) == 0u;
+    const uint32_t n = in_lo ? (uint32_t)ctz32(ndl) >> 3 : (eight ? 8u : 4u + ((uint32_t)ctz32(ndh) >> 3));
+    const uint32_t s8 = n << 3;
+    // the digits right-aligned in eight bytes: v_hi = bytes n-4 .. n-1, v_lo = bytes n-8 .. n-5 (zero in front of byte 0)
+    const uint32_t v_hi = eight ? xh : funnel_r(in_lo ? 0u : xl, in_lo ? xl : xh, s8);
+    const uint32_t v_lo = eight ? xl : (in_lo ? 0u : funnel_r(0u, xl, s8));
+    const uint32_t sep = (eight ? funnel_r(c, 0u, sh) : (in_lo ? rl : rh) >> (s8 & 31u)) & 0xffu;   // (eight digits: the byte behind them)
+    bool bad = ((rl | rh) & H) != 0u;                     // (a byte >= 0x80 would have fooled the digit test)
+    bad |= n == 0u || sep != '\t';
+    out->after = i + n + 1u;
+    out->pos = digits4_value(v_lo) * 10000u + digits4_value(v_hi);
+    return !bad;
+}
+
+// ---- columns 3-6 of a line whose key columns q3_key() took.  ST_OK (out->end / base / fail filled) or ST_DETAIL. --------
+template <class M>
+SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, uint32_t one, Q3Line *out) {
+    const uint32_t H = 0x80808080u;
+    // ---- columns 3-4: one letter, tab, 1..3 digits (not all '0'), tab -- the 8 bytes at offset i -------------------
+    uint32_t x0, x1;
+    {
+        const uint32_t k = i >> 2, sh = i << 3;
+        const uint32_t a = m.ld(k), b = m.ld(k + 1u), c = m.ld(k + 2u);
+        x0 = funnel_r(a, b, sh);
+        x1 = funnel_r(b, c, sh);
+    }
+    const unsigned ref = x0 & 0xffu;
+    bool bad = ((ref | 0x20u) - 'a') >= 26u;              // a letter: '.'/',' stand for REF / ref (pileup.py:255-256)
+    bad |= ((x0 >> 8) & 0xffu) != '\t';
+    const uint32_t d = funnel_r(x0, x1, 16);               // the 4 bytes from the depth column's first
+    const uint32_t y = d ^ 0x30303030u;                    // digits -> 0..9
+    const uint32_t nd = (((y & 0x7f7f7f7fu) + 0x76767676u) | y) & H;   // bit 7: not a digit (exact for any byte)
+    const uint32_t n2 = nd ? (uint32_t)ctz32(nd) >> 3 : 4u;
+    bad |= n2 == 0u || n2 == 4u;                           // (four digits or more: next tier)
+    bad |= ((d >> (8u * (n2 & 3u))) & 0xffu) != '\t';
+    bad |= (y & ((1u << (8u * (n2 & 3u))) - 1u)) == 0u;    // depth 0: pileup.py:226-234, left to the detailed parser
+    if (bad) return ST_DETAIL;
+    const uint32_t b0 = i + 3u + n2;                       // first byte of the bases column
+    // ---- column 5: bases, aligned words -----------------------------------------------------------------
+    const uint32_t refb = (ref | 0x20u) * 0x01010101u;
+    const uint32_t MFD = one * 0xfdfdfdfdu, MF9 = one * 0xf9f9f9f9u;   // (in registers: one LOP3 per masked compare)
+    uint32_t k = b0 >> 2;
+    uint32_t w = m.ld(k);
+    {   // the bytes of the first word in front of the column become a symbol that counts nowhere
+        const uint32_t mk = 0xffffffffu << ((b0 & 3u) * 8u);
+        w = (w & mk) | (0x30303030u & ~mk);
+    }
+    uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', kept '.')
+    uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0, guard = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
+    uint32_t low;
+    for (;;) {
+        low = Q3_NADD(0x5f5f5f5fu, w) & H;                 // bit 7 <-> byte < 0x21
+        if (low) break;
+        guard |= w;
+        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & H;         // '^'
+        const uint32_t part = funnel_l8(prevcar, car);                                       // the byte after a '^'
+        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & H;         // '$'
+        const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);           // bit 7 clear <-> ',' or '.'
+        const uint32_t dck = ~(y2 | part) & H;                                               // kept '.' / ','
+        const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);           // bit 7 clear <-> ) + - /
+        const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);                  // bit 7 clear <-> the reference letter
+        an0 |= ~(y3 | part);                               // an indel sign (or ')' '/': next tier) that is no "^x" quality
+        an1 |= ~(yr | part);                               // the reference letter written out
+        an2 |= car & part;                                 // "^^"
+        a_rem = flag_sum(car | part | dol, a_rem);
+        a_dc = flag_sum(dck, a_dc);
+        a_dot = flag_sum(dck & (w << 6), a_dot);           // bit 1 -> bit 7: '.' not ','
+        prevcar = car;
+        w = m.ld(++k);
+    }
+    uint32_t q0;
+    {   // the word that holds the separator: the same, restricted to the bytes in front of it
+        const uint32_t first = low & (0u - low);
+        const uint32_t valid = (first - 1u) & H;
+        const uint32_t j = (uint32_t)ctz32(first) >> 3;
+        guard |= w & valid;                                // (only the bytes in front of the separator)
+        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & valid;
+        const uint32_t part = funnel_l8(prevcar, car);                     // may reach the separator itself
+        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & valid;
+        const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);
+        const uint32_t dck = ~(y2 | part) & valid;
+        const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);
+        const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);
+        an0 |= ~(y3 | part) & valid;
+        an1 |= ~(yr | part) & valid;
+        an2 |= (car & part) | (part & first);                              // "^" + separator: trailing '^'
+        a_rem = flag_sum((car | part | dol) & valid, a_rem);
+        a_dc = flag_sum(dck, a_dc);
+        a_dot = flag_sum(dck & (w << 6), a_dot);
+        if (((w >> (8u * j)) & 0xffu) != '\t') an2 |= H;                   // the column ends in a tab
+        q0 = 4u * k + j + 1u;
+    }
+    const uint32_t bases_len = q0 - 1u - b0;
+    if (((an0 | an1 | an2 | guard) & H) != 0u || bases_len == 0u) return ST_DETAIL;
+    const uint32_t nb = bases_len - (a_rem >> 7);          // length of the stripped string
+    const uint32_t qe = q0 + nb;                           // where the line has to end
+    if (nb < 1u || qe > limit) return ST_DETAIL;
+    // ---- column 6: as many printable bytes as bases survived, then the line end (pileup.py:248-250) ----
+    {
+        uint32_t kq = q0 >> 2;
+        const uint32_t ke = qe >> 2;
+        uint32_t v = m.ld(kq);
+        const uint32_t mk = 0xffffffffu << ((q0 & 3u) * 8u);
+        v = (v & mk) | (0x30303030u & ~mk);
+        uint32_t acc = H;                                  // bit 7 stays set while every byte is in 0x21..0x7f
+        while (kq + 1u < ke) {                             // two words per step
+            const uint32_t v1 = m.ld(kq + 1u);
+            acc &= Q3_ADD(0x5f5f5f5fu, v) & ~v;
+            acc &= Q3_ADD(0x5f5f5f5fu, v1) & ~v1;
+            kq += 2u;
+            v = m.ld(kq);
+        }
+        if (kq < ke) {
+            acc &= Q3_ADD(0x5f5f5f5fu, v) & ~v;
+            v = m.ld(++kq);
+        }
+        const uint32_t r = qe & 3u;
+        const uint32_t below = (0x80u << (8u * r)) - 1u;   // the bytes in front of the terminator (bit 7 of each)
+        const uint32_t good = Q3_ADD(0x5f5f5f5fu, v) & ~v & H;
+        if ((acc & H) != H || (good & below) != (below & H) || ((v >> (8u * r)) & 0xffu) != '\n') return ST_DETAIL;
+    }
+    // ---- call (pileup.py:550-588): the reference base wins outright ---------------------------------
+    const uint32_t dc = a_dc >> 7, dot = a_dot >> 7;
+    if (dc <= nb - dc) return ST_DETAIL;
+    out->end = qe;
+    out->base = (uint8_t)ref;
+    out->fail = q3_filter(m, nb, dc, dot, dc - dot, p);
+    return ST_OK;
+}
+
+// (rare) the search of q3_find_nl() word by word from offset `from`, once a flagged byte turned out not to be a '\n'
+template <class M>
+SNP_HD_NOINLINE uint32_t q3_find_nl_slow(const M &m, uint32_t from) {
+    uint32_t k = from >> 2;
+    uint32_t w = m.ld(k);
+    const uint32_t mk = 0xffffffffu << ((from & 3u) * 8u);
+    w = (w & mk) | (0x30303030u & ~mk);
+    for (;;) {
+        const uint32_t t = w ^ 0x0a0a0a0au;
+        const uint32_t z = ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;     // exact for any byte values
+        if (z) return 4u * k + ((uint32_t)ctz32(z) >> 3);
+        w = m.ld(++k);
+    }
+}
+
+// position of the first '\n' at or behind offset `from` (the sentinels behind `limit` end the search); *odd (in/out) is
+// set when a byte 0x0b..0x0d (VT, FF, CR) or a byte >= 0x80 lies in front of it in the words looked at.  Exact for any
+// byte values.  Aligned 16-byte chunks: the lanes of a warp step alike, and what follows the loop runs once, converged.
+template <class M>
+SNP_HD uint32_t q3_find_nl(const M &m, uint32_t from, uint32_t one, uint32_t *odd) {
+    const uint32_t H = 0x80808080u;
+    uint32_t c = from >> 4;
+    uint32_t w[4];
+    m.ld4(4u * c, w);
+    {   // bytes in front of `from`: made harmless
+        const uint32_t fw = (from >> 2) & 3u, mk = 0xffffffffu << ((from & 3u) * 8u);
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            const uint32_t keep = j < fw ? 0u : (j == fw ? mk : 0xffffffffu);
+            w[j] = (w[j] & keep) | (0x30303030u & ~keep);
+        }
+    }
+    uint32_t guard = 0;
+    uint32_t in[4];
+    for (;;) {
+        // bit 7 <-> byte (+ a carry from a byte >= 0x80 below it) in 0x0a..0x0d: a true '\n' is always flagged
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) in[j] = Q3_ADD(0x76767676u, w[j]) & Q3_NADD(0x72727272u, w[j]);
+        if (((in[0] | in[1]) | (in[2] | in[3])) & H) break;
+        guard |= w[0] | w[1];
+        guard |= w[2] | w[3];
+        m.ld4(4u * ++c, w);
+    }
+    const uint32_t f0 = in[0] & H, f1 = in[1] & H, f2 = in[2] & H;
+    const uint32_t j = f0 ? 0u : (f1 ? 1u : (f2 ? 2u : 3u));
+    const uint32_t f = f0 ? f0 : (f1 ? f1 : (f2 ? f2 : in[3] & H));
+    const uint32_t wj = f0 ? w[0] : (f1 ? w[1] : (f2 ? w[2] : w[3]));
+    if (j > 0u) guard |= w[0];
+    if (j > 1u) guard |= w[1];
+    if (j > 2u) guard |= w[2];
+    const uint32_t b = (uint32_t)ctz32(f) >> 3;
+    const uint32_t at = 16u * c + 4u * j + b;
+    *odd |= (guard | (wj & ((1u << (8u * b)) - 1u))) & H;               // (bytes behind the flagged one are not part of the guard)
+    if (((wj >> (8u * b)) & 0xffu) == 0x0au) return at;
+    *odd |= H;                                          // VT / FF / CR, or a carry artefact: the exact parser's line
+    return q3_find_nl_slow(m, at + 1u);
+}
+
+// the site of (cached contig, pos) from the packed word of its 32-position group
+SNP_HD void q3_site(const SiteWord &sw, uint32_t bb, int32_t *site, uint32_t *flags) {
+    *site = ((sw.any >> bb) & 1u) ? (int32_t)(sw.rank + (uint32_t)popc32(sw.any & ((1u << bb) - 1u))) : -1;
+    *flags = (((sw.snp >> bb) & 1u) ? SITE_SNP : 0u) | (((sw.exc >> bb) & 1u) ? SITE_EXCLUDED : 0u);
+}
+
+}  // namespace snpgpu

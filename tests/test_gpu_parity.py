@@ -326,6 +326,48 @@ def test_synthetic_sample_device_resident(ctx, genome_len, sample):
     sites.close()
 
 
+@pytest.mark.parametrize("mode_all", [True, False])
+def test_batch_of_samples_one_launch(ctx, mode_all):
+    """snpgpu_pileup_consensus_batch_dev: 19 samples of different lengths (one of them empty) -> two launch sequences;
+    every sample's row, per-line results and stats against the oracle run on that sample alone."""
+    import torch
+    from snp_pipeline_b200 import _lib
+    chrom = "gi|0000000|ref|SYN_5000K.1|"
+    lens = [30000 + 1777 * i for i in range(18)]
+    specs, bufs, ns = [], [], []
+    for i, g in enumerate(lens):
+        spec, buf, n = _synth(ctx, g, 40 + i, pool=max(g // 50, 1))
+        specs.append(spec); bufs.append(buf); ns.append(n)
+    bufs.insert(7, torch.empty(64, dtype=torch.uint8, device="cuda")); ns.insert(7, 0); lens.insert(7, 0); specs.insert(7, None)
+    snp_pos = sorted({int(q) for sp in specs if sp is not None for q in ctx.synth_sample_sites(sp)} | set(range(5, 60000, 997)))
+    snps = [(chrom, q) for q in snp_pos]
+    sites = ctx.sites(snps)
+    p = _lib.make_params(min_cons_depth=3)
+    op = orc.make_params(min_cons_depth=3)
+    B = len(bufs)
+    rows = torch.zeros((B, len(snps)), dtype=torch.uint8, device="cuda")
+    cap = max(lens) + 8
+    lines = torch.zeros((B, cap), dtype=torch.int16, device="cuda")
+    stats = torch.zeros((B, 5), dtype=torch.int64, device="cuda")
+    mode = _lib.MODE_ALL if mode_all else _lib.MODE_SITES
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.pileup_consensus_batch_dev([(bufs[i].data_ptr(), ns[i], rows[i].data_ptr(), lines[i].data_ptr() if mode_all else 0,
+                                     cap if mode_all else 0, stats[i].data_ptr()) for i in range(B)], sites, p, mode)
+    torch.cuda.synchronize()
+    st = stats.cpu().numpy()
+    rows_h, lines_h = rows.cpu().numpy(), lines.cpu().numpy().view(np.uint16)
+    for i in range(B):
+        text = bufs[i][:ns[i]].cpu().numpy()
+        want_row, (cells, fails, _) = orc.pileup_consensus(text, snps, [], op, parse_all=mode_all, want_lines=True)
+        assert st[i, 0] == lens[i] and st[i, 4] == 0, (i, st[i])
+        assert rows_h[i].tobytes() == want_row, i
+        if mode_all:
+            assert np.array_equal(lines_h[i, :lens[i]] & 0xff, cells), i
+            assert np.array_equal(lines_h[i, :lens[i]] >> 8, fails), i
+    ctx.set_stream(None)
+    sites.close()
+
+
 # ------------------------------------------------------------------------------------------ K2
 def test_pipelined_host_calls(ctx):
     """snpgpu_pileup_consensus_begin / _end with one call kept ahead: the same rows, per-line calls and stats as the plain
