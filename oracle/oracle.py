@@ -55,10 +55,10 @@ def make_params(min_base_qual=0, min_cons_freq=0.6, min_cons_depth=1, min_cons_s
 
 
 def build(force=False):
-    """Compile snp_oracle.c (gcc -O2).  Returns the path of the shared object."""
+    """Compile snp_oracle.c (gcc -O3).  Returns the path of the shared object."""
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
         os.makedirs(_BUILD, exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", _SO, _SRC])
+        subprocess.check_call(["gcc", "-O3", "-std=c11", "-fPIC", "-shared", "-o", _SO, _SRC])
     return _SO
 
 
@@ -88,6 +88,9 @@ def lib():
         L.oracle_distance_rows.restype = None
         L.oracle_distance_rows.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p, ctypes.c_size_t,
                                            ctypes.c_size_t]
+        L.oracle_distance_rows_strided.restype = None
+        L.oracle_distance_rows_strided.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p, ctypes.c_size_t,
+                                                   ctypes.c_size_t, ctypes.c_size_t]
         _lib = L
     return _lib
 
@@ -375,6 +378,58 @@ def distance_matrix(rows):
     if n:
         lib().oracle_distance(_ptr(m, ctypes.c_uint8), n, s, _ptr(d, ctypes.c_int32))
     return d
+
+
+def distance_matrix_threads(rows, threads=1):
+    """distance_matrix() with the rows of the upper triangle dealt to `threads` host threads (the C call drops the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(rows)
+    s = len(rows[0]) if n else 0
+    if n == 0 or s == 0 or threads <= 1:
+        return distance_matrix(rows)
+    m = np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(n, s).copy()
+    d = np.zeros((n, n), dtype=np.int32)
+    L = lib()
+    # row i of the triangle costs n - i pairs: interleave the rows so that every thread gets the same share
+
+    def work(t):
+        L.oracle_distance_rows_strided(_ptr(m, ctypes.c_uint8), n, s, _ptr(d, ctypes.c_int32), t, n, threads)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(threads)))
+    return d
+
+
+def hot_path_texts(names, texts, site_lists, params, parse_all=False, threads=1, rows=None):
+    """The path's three files for samples given in sorted order, restated on the CPU: (snplist.txt, snpma.fasta,
+    snp_distance_matrix.tsv) texts.  texts: per sample the pileup bytes (or None when `rows` already holds the
+    consensus rows); site_lists: per sample [(chrom, pos)].  merge_sites.py:94-116 + utils.py:1056-1070,
+    call_consensus.py:161-192, snp_matrix.py:114-119, distance.py:90-115."""
+    from concurrent.futures import ThreadPoolExecutor
+    chroms = sorted({c for s in site_lists for c, _ in s})
+    rank = {c: i for i, c in enumerate(chroms)}
+    per = [list(dict.fromkeys(s)) for s in site_lists]
+    keys = np.array([(rank[c] << 32) | p for s in per for c, p in s], dtype=np.uint64)
+    samp = np.array([i for i, s in enumerate(per) for _ in s], dtype=np.uint32)
+    uniq, cnt, samples = merge_sites_keys(keys, samp)
+    out, o = [], 0
+    sl = samples.tolist()
+    for k, c in zip(uniq.tolist(), cnt.tolist()):
+        out.append("%s\t%d\t%d\t%s\n" % (chroms[k >> 32], k & 0xffffffff, c, "\t".join(names[i] for i in sl[o:o + c])))
+        o += c
+    snplist = "".join(out)
+    snps = [(chroms[k >> 32], k & 0xffffffff) for k in uniq.tolist()]
+    if rows is None:
+        with ThreadPoolExecutor(max_workers=max(threads, 1)) as ex:
+            rows = list(ex.map(lambda t: pileup_consensus(t, snps, [], params, parse_all=parse_all), texts))
+    snpma = "".join(fasta_text(n, r.decode("ascii")) for n, r in zip(names, rows))
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    d = distance_matrix_threads([rows[i] for i in order], threads) if names else np.zeros((0, 0), np.int32)
+    ids = [names[i] for i in order]
+    mat = ["\t%s\n" % "\t".join(ids)]
+    for i, a in enumerate(ids):
+        mat.append("%s\t%s\n" % (a, "\t".join(map(str, d[i].tolist()))))
+    return snplist, snpma, "".join(mat), rows
 
 
 def distance_texts(seqs):
