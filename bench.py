@@ -49,6 +49,11 @@ def parse_args():
     ap.add_argument("--carry", type=float, default=0.05)
     ap.add_argument("--host-pool", type=int, default=4, help="distinct samples kept in pinned host memory for e2e")
     ap.add_argument("--cpu-samples", type=int, default=2, help="samples the cpu_baseline leg parses")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2: BASELINE configs[1] (the default, the metric's configuration); c4: configs[3], 1000 samples "
+                         "sharded over the ranks, files + SHA-256 parity with the oracle; c5: configs[4], distance only")
+    ap.add_argument("--samples-total", type=int, default=0, help="c4 / c5: samples over all ranks (default 1000 / 5000)")
+    ap.add_argument("--out-dir", default="/tmp/snp_pipeline_b200_bench_files")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -353,6 +358,138 @@ def workload_config(args, world):
             "host_pool_samples": args.host_pool, "parallelism": "samples sharded x%d" % world}
 
 
+# ------------------------------------------------------------------------------------------ configs[3]: 1000 samples, files, parity
+def run_c4(args, torch, dist, ctx, rank, world, local_rank, barrier):
+    """BASELINE configs[3] through the package-level driver (snp_pipeline_b200/batch.py, the reference's merge_sites ->
+    call_consensus x N -> snp_matrix -> distance, run.py:691-732, 775-776): samples sharded over the ranks, one all-gather of
+    the site lists, one of the rows; then -- outside the timed region -- the same files from the CPU oracle run over the
+    same synthetic inputs, compared by SHA-256."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    from snp_pipeline_b200 import _lib, batch, sharding
+    from oracle import oracle as orc
+    total = args.samples_total or 1000
+    pool = args.pool_sites if args.pool_sites != 50_000 else 200_000
+    lo, hi = sharding.shard_bounds(total, rank, world)
+    names = ["s%05d" % i for i in range(total)]
+    cap = args.genome_len * 112 + 4096
+    scratch = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    texts, site_pos = [], []
+    for i in range(lo, hi):
+        spec = _lib.SynthSpec(SEED, i, args.genome_len, 24, pool, args.carry, 0.0)
+        nb = ctx.synth_pileup_dev(spec, CONTIG, scratch.data_ptr(), cap)
+        t = torch.empty(nb + 64, dtype=torch.uint8, device="cuda")
+        t[:nb].copy_(scratch[:nb])
+        texts.append(t[:nb])
+        site_pos.append(ctx.synth_sample_sites(spec))
+    del scratch
+    sites = [{CONTIG: sp} for sp in site_pos]
+    params = _lib.make_params(min_cons_depth=3)
+
+    def step(out_dir=None):
+        return batch.run_hot_path(ctx, names[lo:hi], texts, sites, [CONTIG], [args.genome_len], params, out_dir=out_dir,
+                                  mode=_lib.MODE_SITES, dist=dist, rank=rank, world=world)
+
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.enable_timing(True)
+    ctx.kernel_time(0); ctx.kernel_time(1)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    k1_ms, _ = ctx.kernel_time(0)
+    k4_ms, k4_n = ctx.kernel_time(1)
+    ctx.enable_timing(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt.item()) / args.steps
+    res = step(args.out_dir)                                   # once more, with the files (rank 0 writes them)
+    # ---- the oracle over the same inputs: every rank its own samples, rank 0 the union and the distances ----------
+    orc.build()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, cores // world)
+    t0 = time.perf_counter()
+    parts = [None] * world
+    if world > 1:
+        dist.all_gather_object(parts, [sp.astype(np.uint32) for sp in site_pos])
+    else:
+        parts = [site_pos]
+    all_pos = [sp for blk in parts for sp in blk]
+    keys = np.concatenate([sp.astype(np.uint64) for sp in all_pos])
+    samp = np.concatenate([np.full(sp.size, i, dtype=np.uint32) for i, sp in enumerate(all_pos)])
+    uniq, cnt, grouped = orc.merge_sites_keys(keys, samp)
+    snps = [(CONTIG, int(p)) for p in uniq]
+    op = orc.make_params(min_cons_depth=3)
+
+    def one(t):
+        return orc.pileup_consensus(t.cpu().numpy(), snps, [], op, parse_all=False)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        rows = list(ex.map(one, texts))
+    per = (total + world - 1) // world
+    blk = torch.full((per, max(len(snps), 1)), ord("-"), dtype=torch.uint8, device="cuda")
+    if rows:
+        blk[:len(rows), :len(snps)] = torch.from_numpy(np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(len(rows), len(snps)).copy()).cuda()
+    full = sharding.allgather_rows(blk, dist, world)
+    parity = None
+    if rank == 0:
+        rows_all = [bytes(r) for r in full[:total, :len(snps)].cpu().numpy()]
+        want = orc.hot_path_texts(names, None, [[(CONTIG, int(p)) for p in sp] for sp in all_pos], op, threads=cores, rows=rows_all)[:3]
+        parity = {"oracle_seconds": None, "files": {}}
+        ok = True
+        for key, text in zip(("snplist", "snpma", "distance_matrix"), want):
+            got = hashlib.sha256(open(res.files[key], "rb").read()).hexdigest()
+            exp = hashlib.sha256(text.encode()).hexdigest()
+            ok &= got == exp
+            parity["files"][os.path.basename(res.files[key])] = {"sha256": got, "oracle_sha256": exp, "identical": got == exp,
+                                                                  "bytes": os.path.getsize(res.files[key])}
+        parity["identical"] = bool(ok)
+        parity["oracle_seconds"] = time.perf_counter() - t0
+        parity["oracle"] = "oracle/snp_oracle.c: K1 per sample on %d host threads per rank, K2 and K4 on rank 0 (%d threads)" % (threads, cores)
+        assert ok, "C4: the files differ from the oracle's: %r" % parity
+    if rank == 0:
+        positions = total * args.genome_len
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        text_local = float(sum(int(t.numel()) for t in texts))
+        k1_per = k1_ms / max(args.steps * len(texts), 1)
+        ach = (text_local / max(len(texts), 1) + res.n_sites) / (k1_per * 1e-3) / 1e9 if k1_per else None
+        line = {
+            "metric": METRIC, "value": positions / (ms_step * 1e-3), "unit": "positions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: synthetic %d samples x %.1f Mbp sharded over %d GPUs, ~%dk-site pool; "
+                                   "merge_sites -> call_consensus (default mode: lines at snplist positions) -> snp_matrix -> "
+                                   "distance through snp_pipeline_b200.batch.run_hot_path" %
+                                   (total, args.genome_len / 1e6, world, pool // 1000),
+                       "samples_total": total, "samples_per_gpu": len(texts), "genome_len": args.genome_len, "pool_sites": pool,
+                       "l2": "inputs (%.1f GB of text per GPU) exceed L2; no flush needed" % (text_local / 1e9),
+                       "parallelism": "samples sharded x%d, all-gather of site lists + rows" % world},
+            "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k1_pileup_kernel (sites mode)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak if ach else None, "avg_launch_ms": k1_per, "share_of_step": k1_ms / ms if ms else None,
+                         "traffic": None, "k4": {"ms_per_step": k4_ms / max(args.steps, 1), "launches": k4_n}},
+            "cpu_baseline": None, "n_sites": int(res.n_sites), "parity": parity,
+        }
+        print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
@@ -379,13 +516,19 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    w = Workload(ctx, torch, args, rank)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    if args.config == "c4":
+        run_c4(args, torch, dist, ctx, rank, world, local_rank, barrier)
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    w = Workload(ctx, torch, args, rank)
 
     # ---- device-resident: value ------------------------------------------------------------------
     for _ in range(args.warmup):

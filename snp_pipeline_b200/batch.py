@@ -46,13 +46,32 @@ def _chrom_ranks(contigs):
 
 
 def site_keys(positions, rank_of):
-    """[(chrom, pos)] -> uint64 (chrom rank in string order << 32 | pos), duplicates dropped (a set in the reference,
-    utils.py:1127-1131)."""
+    """[(chrom, pos)] -- or {chrom: integer array of positions} -- -> uint64 (chrom rank in string order << 32 | pos),
+    duplicates dropped (a set in the reference, utils.py:1127-1131)."""
+    if isinstance(positions, dict):
+        parts = []
+        for c, pos in positions.items():
+            pos = np.unique(np.asarray(pos, dtype=np.int64))
+            if pos.size and not (0 <= int(pos[0]) and int(pos[-1]) < (1 << 31)):
+                raise ValueError("VCF position outside [0, 2^31)")
+            parts.append((np.uint64(rank_of[c]) << np.uint64(32)) | pos.astype(np.uint64))
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint64)
     seen = dict.fromkeys(positions)
     for _, p in seen:
         if not 0 <= p < (1 << 31):
             raise ValueError("VCF position %d outside [0, 2^31)" % p)
     return np.array([(rank_of[c] << 32) | p for c, p in seen], dtype=np.uint64)
+
+
+def _site_items(site_lists):
+    """(chrom, largest position) pairs of site lists in either form"""
+    for s in site_lists:
+        if isinstance(s, dict):
+            for c, pos in s.items():
+                yield c, (int(np.max(pos)) if len(pos) else 0)
+        else:
+            for c, p in s:
+                yield c, p
 
 
 def snplist_text(chroms, uniq, cnt, samples, names):
@@ -94,7 +113,8 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
 
     local_names   sample names of the block (global order = rank 0's block, rank 1's block, ...)
     local_texts   per sample: a CUDA uint8 tensor holding the pileup file's bytes (16-byte aligned, resident in HBM)
-    local_sites   per sample: [(chrom, pos)] of its variant sites (the positions of var.flt.vcf, utils.py:1113-1132)
+    local_sites   per sample: [(chrom, pos)] of its variant sites (the positions of var.flt.vcf, utils.py:1113-1132),
+                  or {chrom: array of positions}
     contigs       every contig name of the reference, contig_len their lengths (bounds of the site bitmap); None: the
                   contigs the site lists name, each as long as its largest site position
     out_dir       rank 0 writes snplist.txt, snpma.fasta, snp_distance_matrix.tsv there (None: no files)
@@ -104,9 +124,8 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
     dev = torch.device("cuda", torch.cuda.current_device())
     if contigs is None:                                       # (the site lists bound the table: no reference needed)
         seen = {}
-        for s in local_sites:
-            for c, p in s:
-                seen[c] = max(seen.get(c, 0), p)
+        for c, p in _site_items(local_sites):
+            seen[c] = max(seen.get(c, 0), p)
         if world > 1:
             parts = [None] * world
             dist.all_gather_object(parts, seen)
@@ -117,10 +136,9 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
         contigs, contig_len = list(seen), [seen[c] for c in seen]
     chroms, rank_of = _chrom_ranks(contigs)
     len_of = dict(zip(contigs, contig_len))
-    for s in local_sites:
-        for c, _ in s:
-            if c not in rank_of:
-                raise ValueError("variant site on contig %r, which the reference does not hold" % c)
+    for c, _ in _site_items(local_sites):
+        if c not in rank_of:
+            raise ValueError("variant site on contig %r, which the reference does not hold" % c)
     n_local = len(local_names)
     per = n_local
     if world > 1:
