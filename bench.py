@@ -176,7 +176,7 @@ def device_step(w, dist, world):
         local = gu[:n_uniq]
     # the merged list never leaves HBM: K2's sorted unique keys -> the table K1 probes (snpgpu_sites_create_from_keys_dev)
     sites = w.lib.Sites.from_keys_dev(ctx, [CONTIG], [w.args.genome_len], local.data_ptr(), n_uniq)
-    matrix = torch.empty((w.n, max(n_uniq, 1)), dtype=torch.uint8, device="cuda")
+    matrix = torch.empty((w.n, (max(n_uniq, 1) + 63) // 64 * 64), dtype=torch.uint8, device="cuda")    # 16-byte aligned rows
     # one launch sequence per 16 samples (snpgpu_pileup_consensus_batch_dev); every sample has its own per-line results
     ctx.pileup_consensus_batch_dev([(w.texts[i].data_ptr(), w.nbytes[i], matrix[i].data_ptr(), w.lines_dev[i].data_ptr(),
                                      w.args.genome_len + 64, w.stats_dev[i].data_ptr()) for i in range(w.n)],

@@ -240,6 +240,14 @@ int snpgpu_pairwise_distance(snpgpu_ctx *ctx, const uint8_t *matrix, size_t n_ro
                              size_t row_stride, int32_t *dist_out);
 int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
                                  size_t row_stride, size_t row_begin, size_t row_end, int32_t *dist_out_dev);
+/* Whole 64-row tile rows, upper part only: for every entry t of tile_rows (host array) the rows [64 t, 64 t + 64) are
+ * computed from their diagonal tile rightwards -- cells to the left of it are left as they are or zeroed -- into 64 consecutive rows of
+ * dist_out_dev (n_tile_rows x 64 x n_rows int32); the caller mirrors (the distance is symmetric: utils.py:1135-1165
+ * counts positions where the two bases differ).  Multi-GPU drivers deal the tile rows to the ranks in zigzag order, so
+ * that the ranks share the triangle's work evenly and no pair is computed twice. */
+int snpgpu_pairwise_distance_tiles_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
+                                       size_t row_stride, const uint32_t *tile_rows, size_t n_tile_rows,
+                                       int32_t *dist_out_dev);
 
 /* ---- synthetic pileup generator (bench / tests only; SURVEY.md section 8d's input spec).
  *      Writes one sample's pileup text into text_dev (capacity cap bytes) and returns its length.  The text

@@ -26,6 +26,7 @@ EXPORTS = [
     "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end", "snpgpu_pileup_consensus_batch_dev",
     "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_reference_bases",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
+    "snpgpu_pairwise_distance_tiles_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
 ]
 
@@ -148,6 +149,8 @@ def load():
     L.snpgpu_pairwise_distance.argtypes = [vp, vp, sz, sz, sz, vp]
     L.snpgpu_pairwise_distance_dev.restype = ctypes.c_int
     L.snpgpu_pairwise_distance_dev.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp]
+    L.snpgpu_pairwise_distance_tiles_dev.restype = ctypes.c_int
+    L.snpgpu_pairwise_distance_tiles_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp]
     L.snpgpu_synth_pileup_dev.restype = ctypes.c_int
     L.snpgpu_synth_pileup_dev.argtypes = [vp, P(SynthSpec), ctypes.c_char_p, vp, sz, P(sz)]
     L.snpgpu_synth_sample_sites.restype = ctypes.c_int
@@ -429,6 +432,13 @@ class Context(object):
         self._check(self.lib.snpgpu_pairwise_distance_dev(self.handle, ctypes.c_void_p(matrix_ptr), int(n_rows),
                                                           int(n_sites), int(row_stride), int(row_begin),
                                                           int(row_end), ctypes.c_void_p(dist_ptr)))
+
+    def pairwise_distance_tiles_dev(self, matrix_ptr, n_rows, n_sites, row_stride, tile_rows, dist_ptr):
+        """the 64-row tile rows listed in tile_rows, each from its diagonal tile rightwards, 64 output rows per entry"""
+        t = np.ascontiguousarray(tile_rows, dtype=np.uint32)
+        self._check(self.lib.snpgpu_pairwise_distance_tiles_dev(self.handle, ctypes.c_void_p(matrix_ptr), int(n_rows),
+                                                                int(n_sites), int(row_stride), _np_ptr(t), t.size,
+                                                                ctypes.c_void_p(dist_ptr)))
 
     # -- synthetic input (bench / tests) ------------------------------------------------------------
     def synth_pileup_dev(self, spec, contig_name, text_ptr, cap):

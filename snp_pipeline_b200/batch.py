@@ -173,7 +173,7 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
     res.n_sites = n_sites
     # ---- K1 + K3: this block's rows ---------------------------------------------------------------------------------
     sites = _lib.Sites.from_keys_dev(ctx, chroms, [len_of[c] for c in chroms], uniq.data_ptr(), n_sites)
-    width = max(n_sites, 1)
+    width = (max(n_sites, 1) + 63) // 64 * 64                # row stride: 16-byte aligned rows (K4's coalesced pack kernel)
     block = torch.full((per, width), ord("-"), dtype=torch.uint8, device=dev)
     stats = torch.zeros((max(n_local, 1), 5), dtype=torch.int64, device=dev)
     if n_local:
@@ -191,16 +191,29 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
     res.matrix = matrix
     d_host = None
     if distance:
-        stripe = torch.zeros((per, n_rows), dtype=torch.int32, device=dev)
-        if n_sites:
-            ctx.pairwise_distance_dev(matrix.data_ptr(), n_rows, n_sites, width, first, first + per, stripe.data_ptr())
-        if world > 1:
-            full = torch.empty((world * per, n_rows), dtype=torch.int32, device=dev) if rank == 0 else None
-            dist.gather(stripe, [full[r * per:(r + 1) * per] for r in range(world)] if rank == 0 else None, dst=0)
-        else:
-            full = stripe
-        if rank == 0:
+        if world == 1:
+            full = torch.zeros((n_rows, n_rows), dtype=torch.int32, device=dev)
+            if n_sites and n_rows:
+                ctx.pairwise_distance_dev(matrix.data_ptr(), n_rows, n_sites, width, 0, n_rows, full.data_ptr())
             res.distance = full
+        else:
+            # the triangle's 64-row tile rows, dealt in zigzag order: every pair is computed once, on one rank
+            n_tiles = (n_rows + 63) // 64
+            share = [sharding.zigzag_tile_rows(n_rows, r, world) for r in range(world)]
+            most = max(len(x) for x in share)
+            part = torch.zeros((max(most, 1) * 64, n_rows), dtype=torch.int32, device=dev)
+            if n_sites and share[rank]:
+                ctx.pairwise_distance_tiles_dev(matrix.data_ptr(), n_rows, n_sites, width, share[rank], part.data_ptr())
+            parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+            dist.gather(part, parts, dst=0)
+            if rank == 0:
+                upper = torch.zeros((n_tiles, 64, n_rows), dtype=torch.int32, device=dev)
+                for r in range(world):
+                    if share[r]:
+                        upper[torch.tensor(share[r], device=dev)] = parts[r].view(-1, 64, n_rows)[:len(share[r])]
+                upper = upper.view(n_tiles * 64, n_rows)[:n_rows]
+                row = torch.arange(n_rows, device=dev)
+                res.distance = torch.where(row[None, :] >= (row // 64 * 64)[:, None], upper, upper.t())
     sites.close()
     # ---- files (rank 0) ---------------------------------------------------------------------------------------------
     keep = [i for i, nm in enumerate(names) if nm is not None]

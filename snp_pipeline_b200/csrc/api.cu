@@ -822,8 +822,8 @@ int snpgpu_merge_sites(snpgpu_ctx *ctx, const uint64_t *keys, const uint32_t *sa
 }
 
 // ------------------------------------------------------------------------------------------ K4
-int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
-                                 size_t row_stride, size_t row_begin, size_t row_end, int32_t *dist_out_dev) {
+static int k4_run(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites, size_t row_stride,
+                  size_t row_begin, size_t row_end, const uint32_t *tiles, size_t n_tiles, int32_t *dist_out_dev) {
     if (!ctx || (n_rows && n_sites && !matrix_dev) || (n_rows && !dist_out_dev))
         return fail(ctx, SNPGPU_E_ARG, "pairwise_distance: null argument");
     if (row_stride < n_sites || row_begin > row_end || row_end > n_rows)
@@ -834,12 +834,24 @@ int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, siz
     int rc;
     {
         TimedLaunch t(ctx, SNPGPU_KERNEL_DISTANCE);
-        rc = k4_launch(ctx->stream, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, dist_out_dev,
-                       ctx->k4_tmp.p, &launches);
+        rc = k4_launch(ctx->stream, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, tiles, n_tiles, dist_out_dev,
+                       ctx->k4_tmp.p, ctx->n_sms, &launches);
     }
     if (rc) return fail(ctx, rc, "pairwise_distance: launch failed");
     ctx->launches += (uint64_t)launches;
     return SNPGPU_OK;
+}
+
+int snpgpu_pairwise_distance_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
+                                 size_t row_stride, size_t row_begin, size_t row_end, int32_t *dist_out_dev) {
+    return k4_run(ctx, matrix_dev, n_rows, n_sites, row_stride, row_begin, row_end, nullptr, 0, dist_out_dev);
+}
+
+int snpgpu_pairwise_distance_tiles_dev(snpgpu_ctx *ctx, const uint8_t *matrix_dev, size_t n_rows, size_t n_sites,
+                                       size_t row_stride, const uint32_t *tile_rows, size_t n_tile_rows,
+                                       int32_t *dist_out_dev) {
+    if (n_tile_rows && !tile_rows) return fail(ctx, SNPGPU_E_ARG, "pairwise_distance_tiles: null tile list");
+    return k4_run(ctx, matrix_dev, n_rows, n_sites, row_stride, 0, 0, tile_rows ? tile_rows : (const uint32_t *)"", n_tile_rows, dist_out_dev);
 }
 
 int snpgpu_pairwise_distance(snpgpu_ctx *ctx, const uint8_t *matrix, size_t n_rows, size_t n_sites, size_t row_stride,

@@ -39,7 +39,8 @@ int    k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *samp
 // k4_distance.cu
 size_t k4_workspace_bytes(size_t n_rows, size_t n_sites);
 int    k4_launch(cudaStream_t stream, const uint8_t *matrix, size_t n_rows, size_t n_sites, size_t row_stride,
-                 size_t row_begin, size_t row_end, int32_t *dist_out, void *tmp, int *launches);
+                 size_t row_begin, size_t row_end, const uint32_t *tiles, size_t n_tiles, int32_t *dist_out, void *tmp,
+                 int n_sms, int *launches);
 
 // synth.cu
 int    synth_launch(cudaStream_t stream, const snpgpu_synth_spec &spec, const char *contig_name, uint8_t *text_dev,

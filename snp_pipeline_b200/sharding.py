@@ -17,6 +17,19 @@ def shard_bounds(n_items, rank, world):
     return lo, min(lo + per, n_items)
 
 
+def zigzag_tile_rows(n_rows, rank, world, tile=64):
+    """K4's share of a rank: the 64-row tile rows t with zigzag(t) == rank, where zigzag runs 0..world-1, world-1..0, ...
+    Tile row t of the upper triangle holds (T - t) tiles, so a plain block split would leave the last rank nearly
+    idle; pairing a long tile row with a short one gives every rank the same number of tiles to within one row."""
+    n_tiles = (n_rows + tile - 1) // tile
+    out = []
+    for t in range(n_tiles):
+        k = t % (2 * world)
+        if (k if k < world else 2 * world - 1 - k) == rank:
+            out.append(t)
+    return out
+
+
 def allgather_varlen(local, dist, world, pad_value=-1):
     """All-gather of 1-D int64 tensors of different lengths.  Returns the list of per-rank tensors (rank order).
     Two collectives: the counts, then the payload padded to the longest list."""

@@ -535,6 +535,38 @@ def test_distance_random(ctx, n, s, seed):
     assert np.array_equal(got, got.T) and not got.diagonal().any()
 
 
+@pytest.mark.parametrize("n,s,stride", [(70, 4097, 4160), (3, 100, 128), (200, 64, 64), (129, 20000, 20032)])
+def test_distance_aligned_rows_and_tile_list(ctx, n, s, stride):
+    """16-byte aligned rows (K4's coalesced pack kernel), few tiles (the words are dealt to several CTAs), and the
+    tile-row form mirrored into the full matrix -- against the oracle."""
+    import torch
+    rng = np.random.default_rng(n + s)
+    alphabet = np.frombuffer(b"ACGTACGTacgt-NnRY*.", dtype=np.uint8)
+    m = np.full((n, stride), ord("A"), dtype=np.uint8)                      # (the padding must not count)
+    m[:, :s] = alphabet[rng.integers(0, alphabet.size, size=(n, s))]
+    want = orc.distance_matrix([bytes(r[:s]) for r in m])
+    md = torch.from_numpy(m).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        out = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+        ctx.pairwise_distance_dev(md.data_ptr(), n, s, stride, 0, n, out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want)
+        n_tiles = (n + 63) // 64
+        tiles = list(range(n_tiles))[::-1]                                   # any order
+        part = torch.zeros((n_tiles * 64, n), dtype=torch.int32, device="cuda")
+        ctx.pairwise_distance_tiles_dev(md.data_ptr(), n, s, stride, tiles, part.data_ptr())
+        torch.cuda.synchronize()
+        upper = torch.zeros((n_tiles, 64, n), dtype=torch.int32, device="cuda")
+        upper[torch.tensor(tiles, device="cuda")] = part.view(n_tiles, 64, n)
+        upper = upper.view(n_tiles * 64, n)[:n]
+        row = torch.arange(n, device="cuda")
+        full = torch.where(row[None, :] >= (row // 64 * 64)[:, None], upper, upper.t())
+        assert np.array_equal(full.cpu().numpy(), want)
+    finally:
+        ctx.set_stream(None)
+
+
 def test_distance_stripes(ctx):
     """The multi-GPU sharding of K4: row stripes computed separately equal the full matrix."""
     import torch
@@ -577,14 +609,26 @@ def test_distance_full_scale_stripe(ctx):
         assert not torch.diagonal(a[:, :per]).any() and not torch.diagonal(b[:, 3 * per:4 * per]).any()
         assert torch.equal(a[:, 3 * per:4 * per], b[:, :per].T)                  # rank 0's view of rank 3 == rank 3's of rank 0
         assert torch.equal(a[:, :per], a[:, :per].T)
-        valid = torch.zeros(256, dtype=torch.bool, device="cuda")
-        valid[torch.tensor(list(b"ACGTacgt"), device="cuda").long()] = True
+        # a sampled 64 x 64 block of pairs against the oracle (utils.py:1135-1165 restated in C) on the same rows
         rng = random.Random(3)
-        for _ in range(40):
-            i, j = rng.randrange(per), rng.randrange(n)
-            x, y = m[i], m[j]
-            both = valid[x.long()] & valid[y.long()]
-            want = int((both & ((x & 0xdf) != (y & 0xdf))).sum().item())
-            assert int(a[i, j].item()) == want
+        ri = sorted(rng.sample(range(per), 64))
+        rj = sorted(rng.sample(range(n), 64))
+        rows = [bytes(r) for r in m[torch.tensor(ri + rj, device="cuda")].cpu().numpy()]
+        want = orc.distance_matrix(rows)[:64, 64:]
+        got = a[torch.tensor(ri, device="cuda")][:, torch.tensor(rj, device="cuda")].cpu().numpy()
+        assert np.array_equal(got, want)
+        # the tile-row form the multi-GPU driver uses (upper part only, zigzag share of rank 5 of 8) against the stripes
+        from snp_pipeline_b200 import sharding
+        share = sharding.zigzag_tile_rows(n, 5, 8)
+        assert sorted(t for r in range(8) for t in sharding.zigzag_tile_rows(n, r, 8)) == list(range((n + 63) // 64))
+        part = torch.full((len(share) * 64, n), -7, dtype=torch.int32, device="cuda")
+        ctx.pairwise_distance_tiles_dev(m.data_ptr(), n, s, s, share, part.data_ptr())
+        torch.cuda.synchronize()
+        for k, t in enumerate(share):
+            if t * 64 >= 3 * per and t * 64 + 64 <= 4 * per:                  # a tile row inside rank 3's stripe
+                lo = t * 64
+                assert torch.equal(part[k * 64:(k + 1) * 64, lo:], b[lo - 3 * per: lo - 3 * per + 64, lo:])
+                left = part[k * 64:(k + 1) * 64, :lo]
+                assert bool(((left == -7) | (left == 0)).all())               # left of the diagonal tile: untouched or zeroed
     finally:
         ctx.set_stream(None)
