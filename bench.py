@@ -490,6 +490,111 @@ def run_c4(args, torch, dist, ctx, rank, world, local_rank, barrier):
         print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ configs[4]: 5000 samples, distance only
+def run_c5(args, torch, dist, ctx, rank, world, local_rank, barrier):
+    """BASELINE configs[4]: the pairwise SNP-distance matrix of 5000 samples x ~200 k sites (12.5 M pairs) over the ranks.
+    Every rank holds the matrix (in the pipeline: after the row all-gather); the triangle's 64-row tile rows are dealt in
+    zigzag order (sharding.zigzag_tile_rows), each rank computes its share with K4, rank 0 gathers and mirrors."""
+    from snp_pipeline_b200 import sharding
+    from oracle import oracle as orc
+    n = args.samples_total or 5000
+    s_sites = args.pool_sites if args.pool_sites != 50_000 else 200_000
+    stride = (s_sites + 63) // 64 * 64
+    g = torch.Generator(device="cuda").manual_seed(SEED)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    ref = torch.randint(0, 4, (s_sites,), device="cuda", generator=g)
+    alt = (ref + torch.randint(1, 4, (s_sites,), device="cuda", generator=g)) % 4
+    m = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    for lo in range(0, n, 500):                                # (in blocks: the temporaries stay small)
+        hi = min(lo + 500, n)
+        carry = torch.rand((hi - lo, s_sites), device="cuda", generator=g) < 0.05
+        blk = lut[torch.where(carry, alt.expand(hi - lo, -1), ref.expand(hi - lo, -1))]
+        blk[torch.rand((hi - lo, s_sites), device="cuda", generator=g) < 0.03] = ord("-")
+        blk[torch.rand((hi - lo, s_sites), device="cuda", generator=g) < 0.01] = ord("N")
+        m[lo:hi, :s_sites] = blk
+    del carry, blk
+    share = [sharding.zigzag_tile_rows(n, r, world) for r in range(world)]
+    most = max(len(x) for x in share)
+    part = torch.zeros((max(most, 1) * 64, n), dtype=torch.int32, device="cuda")
+    parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 and world > 1 else None
+    n_tiles = (n + 63) // 64
+
+    def step():
+        if share[rank]:
+            ctx.pairwise_distance_tiles_dev(m.data_ptr(), n, s_sites, stride, share[rank], part.data_ptr())
+        if world > 1:
+            dist.gather(part, parts, dst=0)
+        if rank != 0:
+            return None
+        upper = torch.zeros((n_tiles, 64, n), dtype=torch.int32, device="cuda")
+        for r in range(world):
+            if share[r]:
+                src = parts[r] if world > 1 else part
+                upper[torch.tensor(share[r], device="cuda")] = src.view(-1, 64, n)[:len(share[r])]
+        upper = upper.view(n_tiles * 64, n)[:n]
+        row = torch.arange(n, device="cuda")
+        return torch.where(row[None, :] >= (row // 64 * 64)[:, None], upper, upper.t())
+
+    for _ in range(args.warmup):
+        d = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.enable_timing(True)
+    ctx.kernel_time(1)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        d = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    k4_ms, k4_n = ctx.kernel_time(1)
+    ctx.enable_timing(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    tt = torch.tensor([ms, k4_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt[0].item()) / args.steps
+    k4_step = float(tt[1].item()) / args.steps                 # the slowest rank's K4 time per step
+    if rank == 0:
+        assert bool((d == d.t()).all()) and not bool(torch.diagonal(d).any()), "C5: not symmetric with a zero diagonal"
+        rng = np.random.default_rng(7)                          # a sampled 64 x 64 block of pairs against the oracle
+        ri, rj = np.sort(rng.choice(n, 64, replace=False)), np.sort(rng.choice(n, 64, replace=False))
+        rows = [bytes(r) for r in m[torch.from_numpy(np.concatenate([ri, rj])).cuda(), :s_sites].cpu().numpy()]
+        orc.build()
+        want = orc.distance_matrix(rows)[:64, 64:]
+        got = d[torch.from_numpy(ri).cuda()][:, torch.from_numpy(rj).cuda()].cpu().numpy()
+        assert np.array_equal(got, want), "C5: a sampled block differs from the oracle"
+        pairs = n * (n - 1) // 2
+        n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        peak = n_sms * 16 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12   # POPC: 16 lanes / clk / SM, 32 sites per word
+        my_pair_sites = sum((n_tiles - t) for t in share[0]) * 64 * 64 * s_sites  # (rank 0's share, tiles incl. the diagonal ones)
+        line = {
+            "metric": "pairwise SNP-distance matrix: sample pairs x sites per second (BASELINE configs[4])",
+            "value": pairs * s_sites / (ms_step * 1e-3), "unit": "pair-sites/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: synthetic %d samples x %d sites, %d pairs, tile rows of the triangle dealt "
+                                   "zigzag over %d GPUs, gathered and mirrored on rank 0" % (n, s_sites, pairs, world),
+                       "samples_total": n, "n_sites": s_sites, "pairs": pairs,
+                       "l2": "matrix %.2f GB + planes %.2f GB per GPU exceed L2; no flush needed" % (n * stride / 1e9, 3 * n * stride / 8e9),
+                       "parallelism": "tile rows dealt zigzag x%d, one gather" % world},
+            "clocks": clocks, "e2e": None, "gpu_launches": int(launches), "pairs_per_s": pairs / (ms_step * 1e-3),
+            "roofline": {"bound": "issue (POPC: one per pair and 32 sites)", "kernel": "k4_pack_kernel + k4_pairs_kernel",
+                         "achieved": my_pair_sites / (k4_step * 1e-3) / 1e12 if k4_step else None, "peak": peak,
+                         "unit": "T pair-sites/s per GPU", "frac": (my_pair_sites / (k4_step * 1e-3) / 1e12) / peak if k4_step else None,
+                         "k4_ms_per_step": k4_step, "share_of_step": k4_step / ms_step if ms_step else None, "traffic": None,
+                         "peak_source": "n_sms x 16 POPC lanes/clk (profiles/micro/pipes.cu) x 32 sites x SM clock"},
+            "cpu_baseline": None,
+            "parity": {"sampled_block_vs_oracle": "64 x 64 pairs identical", "symmetric_zero_diagonal": True},
+        }
+        print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
@@ -522,8 +627,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    if args.config == "c4":
-        run_c4(args, torch, dist, ctx, rank, world, local_rank, barrier)
+    if args.config in ("c4", "c5"):
+        (run_c4 if args.config == "c4" else run_c5)(args, torch, dist, ctx, rank, world, local_rank, barrier)
         ctx.close()
         if world > 1:
             dist.destroy_process_group()

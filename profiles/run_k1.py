@@ -21,6 +21,9 @@ cap = G * 112 + 4096
 buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
 n = ctx.synth_pileup_dev(spec, "gi|0000000|ref|SYN_5000K.1|", buf.data_ptr(), cap)
 pos = ctx.synth_sample_sites(spec)
+extra = int(os.environ.get("EXTRA_SITES", "0"))          # a union as large as a big batch's: more lines at sites
+if extra:
+    pos = np.union1d(pos, np.random.default_rng(1).choice(G, extra, replace=False).astype(pos.dtype) + 1)
 sites = _lib.Sites.from_arrays(ctx, ["gi|0000000|ref|SYN_5000K.1|"], np.zeros(pos.size, np.int32), pos.astype(np.int64))
 B = int(os.environ.get("BATCH", "8"))                     # samples per launch (the same text, separate outputs)
 row = torch.empty((B, max(pos.size, 1)), dtype=torch.uint8, device="cuda")

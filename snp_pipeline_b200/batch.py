@@ -51,8 +51,10 @@ def site_keys(positions, rank_of):
     if isinstance(positions, dict):
         parts = []
         for c, pos in positions.items():
-            pos = np.unique(np.asarray(pos, dtype=np.int64))
-            if pos.size and not (0 <= int(pos[0]) and int(pos[-1]) < (1 << 31)):
+            pos = np.asarray(pos, dtype=np.int64)
+            if pos.size > 1 and not bool(np.all(pos[1:] > pos[:-1])):      # (VCF order: already strictly rising)
+                pos = np.unique(pos)
+            if pos.size and not (0 <= int(pos.min()) and int(pos.max()) < (1 << 31)):
                 raise ValueError("VCF position outside [0, 2^31)")
             parts.append((np.uint64(rank_of[c]) << np.uint64(32)) | pos.astype(np.uint64))
         return np.concatenate(parts) if parts else np.zeros(0, np.uint64)

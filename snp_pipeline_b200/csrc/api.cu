@@ -254,6 +254,7 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
     size_t s_flags = add(h.flags.data(), h.flags.size());
     size_t s_words = add(h.words.data(), h.words.size() * sizeof(SiteWord));
     size_t s_su = add(h.snp_unique.data(), h.snp_unique.size() * 4);
+    size_t s_q3 = add(h.q3rows.data(), h.q3rows.size() * 4);
     snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
     if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create: host allocation");
     cudaError_t e = cudaMalloc(&s->blob, total);
@@ -274,6 +275,7 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
     s->table.max_pos = (const int64_t *)at(s_max); s->table.bits = (const uint32_t *)at(s_bits);
     s->table.rank = (const uint32_t *)at(s_rank); s->table.flags = (const uint8_t *)at(s_flags);
     s->table.words = (const SiteWord *)at(s_words);
+    s->table.q3rows = (const uint32_t *)at(s_q3);
     s->snp_unique = (int32_t *)at(s_su);
     *out = s;
     return SNPGPU_OK;
@@ -330,6 +332,7 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
     const size_t o_len1 = put(h.len1.data(), h.len1.size() * 4), o_names = put(h.names.data(), h.names.size());
     const size_t o_noff = put(h.name_off.data(), h.name_off.size() * 4), o_base = put(h.bit_base.data(), h.bit_base.size() * 8);
     const size_t o_max = put(h.max_pos.data(), h.max_pos.size() * 8);
+    const size_t o_q3 = put(h.q3rows.data(), h.q3rows.size() * 4);
     const size_t small = stage.size();
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_bits = small, o_rank = o_bits + up(n_words * 4), o_flags = o_rank + up(n_words * 4);
@@ -373,6 +376,7 @@ int snpgpu_sites_create_from_keys_dev(snpgpu_ctx *ctx, const char *contig_names,
     s->table.max_pos = (const int64_t *)at(o_max); s->table.bits = (const uint32_t *)at(o_bits);
     s->table.rank = (const uint32_t *)at(o_rank); s->table.flags = at(o_flags);
     s->table.words = (const SiteWord *)at(o_words);
+    s->table.q3rows = (const uint32_t *)at(o_q3);
     s->snp_unique = (int32_t *)at(o_su);
     *out = s;
     return SNPGPU_OK;

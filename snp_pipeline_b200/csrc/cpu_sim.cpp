@@ -24,6 +24,8 @@ struct HostWin {                // line_quick3.cuh's memory policy over a plain 
     uint32_t ld(uint32_t k) const { return p[k]; }
     uint32_t tab16(uint32_t k) const { return tab[k]; }
     void ld4(uint32_t k, uint32_t *w) const { w[0] = p[k]; w[1] = p[k + 1]; w[2] = p[k + 2]; w[3] = p[k + 3]; }
+    uint32_t row(uint32_t k) const { return p[k]; }
+    void row4(uint32_t k, uint32_t *w) const { ld4(k, w); }
 };
 
 extern "C" {
@@ -84,16 +86,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
             } else {                                                     // the steps of k1_pileup.cu's lane loop
                 if (cc3_cid != hint) {                                   // (the kernel follows the tile's first line)
                     const uint32_t L = (uint32_t)(t.name_off[hint + 1] - t.name_off[hint]) + 1u;
-                    auto name_at = [&](uint32_t idx) { return t.names[t.name_off[hint] + idx]; };
-                    const uint32_t nw = ((L + 6u) >> 2) < 3u ? 3u : (L + 6u) >> 2;
-                    for (uint32_t a = 0; a < 4u; a++) {
-                        uint32_t dummy;
-                        for (uint32_t j = 0; j < Q3_NAMEW; j++) q3_row_word(name_at, L, a, j, &rows[a * Q3_NAMEW + j], &dummy);
-                        for (uint32_t j = 0; j < 8u; j++) q3_row_word(name_at, L, a, j, &dummy, &rows[Q3_MASK8_W + 8u * a + j]);
-                        q3_row_word(name_at, L, a, 0u, &dummy, &rows[Q3_MASKC_W + 4u * a]);
-                        q3_row_word(name_at, L, a, nw - 2u, &dummy, &rows[Q3_MASKC_W + 4u * a + 1u]);
-                        q3_row_word(name_at, L, a, nw - 1u, &dummy, &rows[Q3_MASKC_W + 4u * a + 2u]);
-                    }
+                    for (uint32_t k = 0; k < Q3_ROWS_WORDS; k++) rows[k] = t.q3rows[(size_t)hint * SITE_Q3ROWS_WORDS + k];   // (as build_host_sites made them)
                     q3_contig_set(&cc3, rows_w, L, hint, t.max_pos[hint], t.bit_base[hint]);
                     cc3_cid = hint;
                 }

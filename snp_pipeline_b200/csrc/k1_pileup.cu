@@ -44,12 +44,16 @@ struct SmemWin {                                // line_quick3.cuh's memory poli
         const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(k1_smem_raw) + base_w + k);
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
+    __device__ __forceinline__ uint32_t row(uint32_t k) const { return ld(k); }        // (the name rows live in the slice too)
+    __device__ __forceinline__ void row4(uint32_t k, uint32_t *w) const { ld4(k, w); }
     __device__ __forceinline__ uint32_t tab16(uint32_t k) const { return reinterpret_cast<const uint16_t *>(k1_smem_raw)[k]; }
     __device__ __forceinline__ uint32_t byte(uint32_t off) const { return k1_smem_raw[4u * base_w + off]; }
 };
 
-// queue entry, second word: sample | flags << 32
+// queue entry, second word: sample | flags << 32 | (contig of the line + 1, when its key columns were taken) << 40
 enum : unsigned long long { K1_Q_GENERAL = 1ull << 32 };     // odd bytes seen: straight to line_general.cuh
+constexpr unsigned long long K1_Q_EMPTY = ~0ull;             // first word of a slot its warp claimed and did not fill
+constexpr int K1_QBLOCK = 64;                                // queue entries a warp claims at a time
 
 // The contig of the line at offset s of the window (byte-wise; once per tile at most): loads the warp's cache with it.
 // A name the site table does not hold is cached all the same (cid -1, no sites: its lines are parsed / skipped like any
@@ -66,20 +70,9 @@ __device__ __noinline__ void k1_follow_contig(const SiteTable &t, const SmemWin 
     const uint32_t L = n + 1u;
     const int lane = threadIdx.x & 31;
     auto name_at = [&](uint32_t idx) { return m.byte(s + idx); };
-    const uint32_t nw = ((L + 6u) >> 2) < 3u ? 3u : (L + 6u) >> 2;
     uint32_t w[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const uint32_t idx = (uint32_t)lane + 32u * r;          // 128 words: names [4][20], masks [4][8], masks [4][4]
-        uint32_t v = 0, mk = 0;
-        if (idx < Q3_MASK8_W) q3_row_word(name_at, L, idx / Q3_NAMEW, idx % Q3_NAMEW, &v, &mk);
-        else if (idx < Q3_MASKC_W) { q3_row_word(name_at, L, (idx - Q3_MASK8_W) >> 3, (idx - Q3_MASK8_W) & 7u, &mk, &v); }
-        else {
-            const uint32_t a = (idx - Q3_MASKC_W) >> 2, which = (idx - Q3_MASKC_W) & 3u;
-            q3_row_word(name_at, L, a, which == 0u ? 0u : (which == 3u ? 0u : nw - 3u + which), &mk, &v);
-        }
-        w[r] = v;
-    }
+    for (int r = 0; r < 4; r++) w[r] = q3_rows_word(name_at, L, (uint32_t)lane + 32u * r);     // 128 words, four per lane
     __syncwarp();
     uint32_t *rows = reinterpret_cast<uint32_t *>(k1_smem_raw + 4u * m.base_w + K1_SLICE_ROWS);
 #pragma unroll
@@ -116,6 +109,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
     if (lane == 0) ticket = (int)atom_inc_u32(g.next_tile);
     int si = 0;                                               // sample of the previous tile (tickets rise: so do samples)
     uint32_t acc_lines = 0, acc_ok = 0;                       // lines / parsed lines of sample si not yet added to its status
+    // the follow-up kernel's queue is claimed K1_QBLOCK entries at a time: one atomic per block, not per warp-step (with a
+    // large snplist nearly every step of the sites mode queues a line); slots a warp leaves unused are marked empty
+    unsigned long long q_base = 0;
+    uint32_t q_used = K1_QBLOCK;
     for (;;) {
         const int t = __shfl_sync(0xffffffffu, ticket, 0);
         if (t >= g.total_tiles) break;
@@ -195,7 +192,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         uint32_t cnt = 0, n_ok = 0;
         while (__any_sync(0xffffffffu, have)) {
             bool push = false;
-            uint32_t push_len = 0, push_flag = 0, nxt = 0;
+            uint32_t push_len = 0, push_flag = 0, push_cid = 0, nxt = 0;
             if (have) {
                 uint32_t next;
                 Q3Line q;
@@ -242,6 +239,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                     const bool at_site = known && ((g.sites.bits[widx] >> bb) & 1u);
                     if (!keyok || odd || at_site || (e >= wlen && !eof)) {
                         push = true;
+                        push_cid = keyok ? (uint32_t)(cc.cid + 1) : 0u;
                         push_len = e < wlen || eof ? e - s : 0u;
                         push_flag = (odd || (e >= wlen && !eof)) ? 1u : 0u;
                     }
@@ -251,13 +249,20 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             }
             const uint32_t pb = __ballot_sync(0xffffffffu, push);
             if (pb) {                                         // declined lines -> the follow-up kernel's queue
-                unsigned long long slot = 0;
-                if (lane == 0) slot = atomicAdd(g.queue_count, (unsigned long long)__popc(pb));
-                slot = __shfl_sync(0xffffffffu, slot, 0) + (unsigned long long)__popc(pb & ((1u << lane) - 1u));
+                const uint32_t np = (uint32_t)__popc(pb);
+                if (q_used + np > (uint32_t)K1_QBLOCK) {      // the block is full: mark its tail empty, claim the next one
+                    for (uint32_t k = q_used + (uint32_t)lane; k < (uint32_t)K1_QBLOCK; k += 32u)
+                        if (q_base + k < g.queue_cap) g.queue[2ull * (q_base + k)] = K1_Q_EMPTY;
+                    if (lane == 0) q_base = atomicAdd(g.queue_count, (unsigned long long)K1_QBLOCK);
+                    q_base = __shfl_sync(0xffffffffu, q_base, 0);
+                    q_used = 0;
+                }
+                const unsigned long long slot = q_base + q_used + (unsigned long long)__popc(pb & ((1u << lane) - 1u));
                 if (push && slot < g.queue_cap) {
                     g.queue[2ull * slot] = k1_entry(cnt, push_len, base + s);
-                    g.queue[2ull * slot + 1ull] = (unsigned long long)si | (push_flag ? K1_Q_GENERAL : 0ull);
+                    g.queue[2ull * slot + 1ull] = (unsigned long long)si | (push_flag ? K1_Q_GENERAL : 0ull) | ((unsigned long long)push_cid << 40);
                 }
+                q_used += np;
             }
             if (have) {
                 cnt++;
@@ -281,6 +286,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         atomicAdd(&g.s[si].st->n_lines, (unsigned long long)acc_lines);
         if (acc_ok) atomicAdd(&g.s[si].st->n_parsed, (unsigned long long)acc_ok);
     }
+    for (uint32_t k = q_used + (uint32_t)lane; k < (uint32_t)K1_QBLOCK; k += 32u)      // the unused tail of the warp's last block
+        if (q_base + k < g.queue_cap) g.queue[2ull * (q_base + k)] = K1_Q_EMPTY;
 }
 
 // ---- the follow-up kernel: the queued lines, one thread per line, through the second and third tier ---------------
@@ -292,8 +299,61 @@ __device__ __forceinline__ void k1_sample_args(const K1Batch &g, uint32_t si, Pi
     a->arena = g.arena; a->arena_cap = g.arena_cap; a->arena_st = g.s[0].st;
 }
 
+// line_quick3.cuh's memory policy over the text where it lies in global memory (the follow-up kernel): words relative to
+// a 16-byte aligned base in front of the line, name rows from the site table, filter tables in shared memory
+struct GmemWin {
+    const uint32_t *p;
+    const uint32_t *rows;
+    const uint16_t *tab;
+    __device__ __forceinline__ uint32_t ld(uint32_t k) const { return __ldg(p + k); }
+    __device__ __forceinline__ void ld4(uint32_t k, uint32_t *w) const {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + k));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    __device__ __forceinline__ uint32_t row(uint32_t k) const { return __ldg(rows + k); }
+    __device__ __forceinline__ void row4(uint32_t k, uint32_t *w) const {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rows + k));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    __device__ __forceinline__ uint32_t tab16(uint32_t k) const { return tab[k]; }
+};
+
+// A queued line whose key columns the pileup kernel took (sites mode: a line at a site) through the first tier again,
+// densely -- 32 such lines per warp.  true: decided (cell stored); false: on to the second tier.
+__device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S, const uint16_t *tab, uint32_t cid,
+                                              unsigned long long goff, uint32_t len, uint32_t one) {
+    if (len == 0u || goff + (unsigned long long)len + 48ull > S.nbytes) return false;     // (the words read reach past the line)
+    const unsigned long long abase = goff & ~15ull;
+    const GmemWin m{reinterpret_cast<const uint32_t *>(S.text + abase), g.sites.q3rows + (size_t)cid * SITE_Q3ROWS_WORDS, tab};
+    const uint32_t s = (uint32_t)(goff - abase), limit = s + len;      // (the line's own '\n' stands where the sentinels would)
+    Q3Contig cc;
+    q3_contig_set(&cc, 0u, (uint32_t)g.sites.len1[cid], (int32_t)cid, g.sites.max_pos[cid], g.sites.bit_base[cid]);
+    Q3Line q;
+    if (!q3_key(m, s, limit, cc, one, &q)) return false;
+    if ((int32_t)q.pos > cc.max_pos) return false;
+    const uint32_t widx = cc.word_base + (q.pos >> 5), bb = q.pos & 31u;
+    const SiteWord sw = load_site_word(g.sites.words + widx);
+    if (!((sw.any >> bb) & 1u)) return false;
+    if (q3_rest(m, q.after, limit, g.p, one, &q) != ST_OK || q.end != limit) return false;
+    unsigned fail = q.fail;
+    if ((sw.exc >> bb) & 1u) fail |= FAIL_REGION;
+    const unsigned cell = fail ? (unsigned)'-' : q.base;
+    if ((sw.snp >> bb) & 1u) {
+        const uint32_t site = sw.rank + (uint32_t)__popc(sw.any & ((1u << bb) - 1u));
+        atomicMax(&S.site_cells[site], ((goff + 1ull) << 8) | (unsigned long long)cell);
+    }
+    if (S.rec_off) {                                          // the VCF pass wants to know which lines were parsed
+        const unsigned long long k = atomicAdd(S.rec_count, 1ull);
+        if (k < S.rec_cap) S.rec_off[k] = goff;
+    }
+    return true;
+}
+
 template <bool HAS_QUAL>
 __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1Batch g) {
+    __shared__ uint16_t tab[2 * Q3_TABN];
+    for (uint32_t k = threadIdx.x; k < 2u * Q3_TABN; k += blockDim.x) tab[k] = (uint16_t)q3_tab_entry(k, g.p);
+    __syncthreads();
     unsigned long long n = *g.queue_count;
     if (n > g.queue_cap) n = g.queue_cap;                     // (more than fit: the finish kernel reports it)
     K1Cold cs{0, 0u, 0u};
@@ -301,7 +361,19 @@ __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1
     uint32_t cur = 0xffffffffu;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long e0 = g.queue[2ull * i], e1 = g.queue[2ull * i + 1ull];
+        const unsigned long long e0 = g.queue[2ull * i];
+        if (e0 == K1_Q_EMPTY) continue;
+        const unsigned long long e1 = g.queue[2ull * i + 1ull];
+        const uint32_t cid1 = (uint32_t)(e1 >> 40);
+        const bool quick = !HAS_QUAL && g.mode == SNPGPU_MODE_SITES && cid1 != 0u && !(e1 & K1_Q_GENERAL) &&
+                           k1_rest_quick(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), g.one);
+        {   // one add per warp and sample, not one per line
+            const uint32_t act = __activemask();
+            const uint32_t same = __match_any_sync(act, quick ? (uint32_t)e1 : 0xffffffffu);
+            if (quick && (int)(threadIdx.x & 31u) == __ffs((int)same) - 1)
+                atomicAdd(&g.s[(uint32_t)e1].st->n_parsed, (unsigned long long)__popc(same));
+        }
+        if (quick) continue;
         if ((uint32_t)e1 != cur) { cur = (uint32_t)e1; k1_sample_args(g, cur, &a); }
         cs.n_parsed = cs.n_general = 0u;
         bool more = true;

@@ -15,9 +15,10 @@
 // constants with IMAD (multiplier `one`, a kernel parameter the compiler cannot fold) and count flags with IDP.4A, which
 // leaves the ALU pipe the logic only.  FLO / POPC (quarter rate) stay out of the loops.
 //
-// Memory: the parser reads the staged text through a policy object M with  uint32_t ld(uint32_t word)  -- word `word` of
-// the warp's slice of shared memory (device) or of a plain array (tests/cpu_sim): aligned 32-bit loads only, 32-bit
-// addressing, and the compiler always knows the address space.  Preconditions: '\n' sentinels in bytes
+// Memory: the parser reads the text through a policy object M -- ld(word) / ld4(word, out[4]) for the text's aligned words,
+// row(word) / row4(word, out[4]) for the cached contig's name rows, tab16(i) for the filter tables: the warp's slice of
+// shared memory in the pileup kernel, the text in global memory + tables in shared memory in its follow-up kernel, plain
+// arrays in tests/cpu_sim -- aligned loads only, 32-bit addressing, and the compiler always knows the address space.  Preconditions: '\n' sentinels in bytes
 // [limit, limit + QUICK_PAD) of the window.  Any byte values are safe: every word that takes part in a SWAR test is OR-ed
 // into a guard, and a byte >= 0x80 declines the line.
 #pragma once
@@ -29,6 +30,7 @@ constexpr uint32_t Q3_NAMEW = 20;      // words per alignment row of the cached 
 constexpr uint32_t Q3_MASK8_W = 4u * Q3_NAMEW;             // word offset of the [4][8] masks of the first eight words
 constexpr uint32_t Q3_MASKC_W = Q3_MASK8_W + 32u;           // ... of the [4][4] masks of words 0, nw - 2, nw - 1 (longer names)
 constexpr uint32_t Q3_ROWS_WORDS = Q3_MASKC_W + 16u;
+static_assert(Q3_ROWS_WORDS == SITE_Q3ROWS_WORDS, "sites.cuh keeps one block of rows per contig");
 
 // The contig a warp currently expects.  rows: [4][Q3_NAMEW] words of name + '\t' shifted right by a = 0..3 bytes (what
 // the aligned words of a line that starts at byte a of a word look like); then [4][8] masks of the bytes that count in the
@@ -56,6 +58,18 @@ SNP_HD void q3_row_word(const F &name_at, uint32_t L, uint32_t a, uint32_t j, ui
         }
     }
     *w = v; *mk = m;
+}
+
+// word idx (0 .. Q3_ROWS_WORDS) of a contig's block of rows: names [4][Q3_NAMEW], masks [4][8], masks [4][4]
+template <class F>
+SNP_HD uint32_t q3_rows_word(const F &name_at, uint32_t L, uint32_t idx) {
+    const uint32_t nw = ((L + 6u) >> 2) < 3u ? 3u : (L + 6u) >> 2;
+    uint32_t v = 0, mk = 0;
+    if (idx < Q3_MASK8_W) { q3_row_word(name_at, L, idx / Q3_NAMEW, idx % Q3_NAMEW, &v, &mk); return v; }
+    if (idx < Q3_MASKC_W) { q3_row_word(name_at, L, (idx - Q3_MASK8_W) >> 3, (idx - Q3_MASK8_W) & 7u, &v, &mk); return mk; }
+    const uint32_t a = (idx - Q3_MASKC_W) >> 2, which = (idx - Q3_MASKC_W) & 3u;
+    q3_row_word(name_at, L, a, which == 0u || which == 3u ? 0u : nw - 3u + which, &v, &mk);
+    return mk;
 }
 
 SNP_HD void q3_contig_set(Q3Contig *cc, uint32_t rows_w, uint32_t L, int32_t cid, int64_t max_pos, int64_t bit_base) {
@@ -114,8 +128,8 @@ SNP_HD bool q3_name(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc) 
     uint32_t diff;
     if (cc.nw <= 8u) {                                  // (warp-uniform) eight masked words, all loads up front
         uint32_t n[8], mk[8], t[8];
-        m.ld4(r, n); m.ld4(r + 4u, n + 4);
-        m.ld4(cc.rows_w + Q3_MASK8_W + 8u * a, mk); m.ld4(cc.rows_w + Q3_MASK8_W + 8u * a + 4u, mk + 4);
+        m.row4(r, n); m.row4(r + 4u, n + 4);
+        m.row4(cc.rows_w + Q3_MASK8_W + 8u * a, mk); m.row4(cc.rows_w + Q3_MASK8_W + 8u * a + 4u, mk + 4);
 #pragma unroll
         for (uint32_t j = 0; j < 8u; j++) t[j] = m.ld(k0 + j);
 #pragma unroll
@@ -123,10 +137,10 @@ SNP_HD bool q3_name(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc) 
         diff = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
     } else {
         const uint32_t q = cc.rows_w + Q3_MASKC_W + 4u * a, nw = cc.nw;
-        diff = (m.ld(k0) ^ m.ld(r)) & m.ld(q);
-        for (uint32_t j = 1u; j + 2u < nw; j++) diff |= m.ld(k0 + j) ^ m.ld(r + j);
-        diff |= (m.ld(k0 + nw - 2u) ^ m.ld(r + nw - 2u)) & m.ld(q + 1u);
-        diff |= (m.ld(k0 + nw - 1u) ^ m.ld(r + nw - 1u)) & m.ld(q + 2u);
+        diff = (m.ld(k0) ^ m.row(r)) & m.row(q);
+        for (uint32_t j = 1u; j + 2u < nw; j++) diff |= m.ld(k0 + j) ^ m.row(r + j);
+        diff |= (m.ld(k0 + nw - 2u) ^ m.row(r + nw - 2u)) & m.row(q + 1u);
+        diff |= (m.ld(k0 + nw - 1u) ^ m.row(r + nw - 1u)) & m.row(q + 2u);
     }
     return diff == 0u;
 }

@@ -31,7 +31,9 @@ struct SiteTable {
     const uint32_t *rank;
     const uint8_t  *flags;      // n_unique
     const SiteWord *words;      // the same facts packed per bitmap word (bits / flags / rank remain for the other tiers)
+    const uint32_t *q3rows;     // per contig SITE_Q3ROWS_WORDS words: the name rows / masks of line_quick3.cuh's Q3Contig
 };
+constexpr uint32_t SITE_Q3ROWS_WORDS = 128;
 
 // index of (contig, pos) among the unique sites, or -1
 SNP_HD int32_t site_find(const SiteTable &t, int cid, int64_t pos) {

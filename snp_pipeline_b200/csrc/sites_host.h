@@ -6,8 +6,14 @@
 #include <string.h>
 #include <vector>
 #include "sites.cuh"
+#include "line_quick3.cuh"
 
 namespace snpgpu {
+
+struct HostNameAt {                         // (a functor, not a lambda: nvcc compiles this header for api.cu too)
+    const char *nm;
+    SNP_HD uint8_t operator()(uint32_t i) const { return (uint8_t)nm[i]; }
+};
 
 struct HostSites {
     int32_t n_contigs = 0;
@@ -20,6 +26,7 @@ struct HostSites {
     std::vector<uint8_t>  flags;
     std::vector<SiteWord> words;
     std::vector<int32_t>  snp_unique;       // unique-site index of snplist entry k
+    std::vector<uint32_t> q3rows;           // per contig: line_quick3.cuh's name rows
 
     SiteTable view() const {
         SiteTable t;
@@ -28,6 +35,7 @@ struct HostSites {
         t.names = names.data(); t.name_off = name_off.data();
         t.bit_base = bit_base.data(); t.max_pos = max_pos.data();
         t.bits = bits.data(); t.rank = rank.data(); t.flags = flags.data(); t.words = words.data();
+        t.q3rows = q3rows.data();
         return t;
     }
 };
@@ -108,6 +116,14 @@ inline int build_host_sites(const char *contig_names, const int32_t *name_off, i
         e.push_back('\t');
         while (e.size() % 4) e.push_back('\0');
         for (size_t i = 0; i < e.size(); i += 4) { uint32_t w; memcpy(&w, e.data() + i, 4); h.names4.push_back(w); }
+    }
+    h.q3rows.assign(nc1 * SITE_Q3ROWS_WORDS, 0u);
+    for (int c = 0; c < n_contigs; c++) {
+        const uint32_t L = (uint32_t)(name_off[c + 1] - name_off[c]) + 1u;
+        if (((L + 6u) >> 2) > Q3_NAMEW) continue;           // (a name too long for the first tier: never cached)
+        const char *nm = contig_names + name_off[c];
+        const HostNameAt name_at{nm};
+        for (uint32_t k = 0; k < SITE_Q3ROWS_WORDS; k++) h.q3rows[(size_t)c * SITE_Q3ROWS_WORDS + k] = q3_rows_word(name_at, L, k);
     }
     h.off4[n_contigs] = (int32_t)h.names4.size();
     h.names4.push_back(0); h.names4.push_back(0);
