@@ -186,6 +186,7 @@ def device_step(w, dist, world):
     d = torch.empty((w.n, full.shape[0]), dtype=torch.int32, device="cuda")
     ctx.pairwise_distance_dev(full.data_ptr(), full.shape[0], n_uniq, full.shape[1], lo, lo + w.n, d.data_ptr())
     sites.close()
+    w.full_matrix = full                                       # (every rank's rows: the N > 1 parity check reads it)
     return n_uniq, matrix, d
 
 
@@ -680,6 +681,20 @@ def main():
         dist.all_gather_into_tensor(full_d, d.contiguous())            # the ranks' row stripes, in rank order
         assert bool((full_d == full_d.T).all()) and not bool(torch.diagonal(full_d).any()), \
             "the distance matrix assembled from the ranks' stripes is not symmetric with a zero diagonal"
+        if rank == 0 and not args.no_cpu:
+            # ... and against the oracle: rank 0's first two rows under the GLOBAL site list, and a block of distances
+            # between its first 16 rows and 64 rows sampled from all ranks
+            from oracle import oracle as orc
+            orc.build()
+            snps_g = [(CONTIG, int(p)) for p in keys_now.cpu().numpy()]
+            for i in range(min(2, w.n)):
+                row = orc.pileup_consensus(w.texts[i][:w.nbytes[i]].cpu().numpy(), snps_g, [], orc.make_params(min_cons_depth=3), parse_all=True)
+                assert row == matrix_host[i].tobytes(), "N > 1: the oracle's row %d differs from the GPU's" % i
+            cols = np.sort(np.random.default_rng(11).choice(world * w.n, min(64, world * w.n), replace=False))
+            fm = w.full_matrix[:, :n_sites].cpu().numpy()
+            rows_o = [bytes(r) for r in fm[:16]] + [bytes(fm[c]) for c in cols]
+            want = orc.distance_matrix(rows_o)[:16, 16:]
+            assert np.array_equal(d_host[:16][:, cols], want), "N > 1: a sampled block of distances differs from the oracle's"
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peaks = {}

@@ -212,6 +212,11 @@ typedef struct {
     uint8_t  pad[3];
 } snpgpu_vcf_alt;
 
+/* Tell the context that snpgpu_pileup_vcf_records will follow the next snpgpu_pileup_consensus calls (call_consensus
+ * --vcfFileName, which run.py:709 always passes): in SNPGPU_MODE_SITES the call then lists the lines it parsed on the
+ * way (they go through the follow-up kernel anyway) and K5 does not have to run K1 a second time. */
+int snpgpu_pileup_want_vcf_records(snpgpu_ctx *ctx, int on);
+
 int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
                               snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec,
                               snpgpu_vcf_alt *alt_out, size_t alt_cap, size_t *n_alt);

@@ -24,7 +24,7 @@ EXPORTS = [
     "snpgpu_kernel_time", "snpgpu_sites_create", "snpgpu_sites_create_from_keys_dev",
     "snpgpu_sites_destroy", "snpgpu_sites_n_snp", "snpgpu_pileup_consensus", "snpgpu_pileup_consensus_dev",
     "snpgpu_pileup_consensus_begin", "snpgpu_pileup_consensus_end", "snpgpu_pileup_consensus_batch_dev",
-    "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_reference_bases",
+    "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_pileup_want_vcf_records", "snpgpu_reference_bases",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_pairwise_distance_tiles_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
@@ -139,6 +139,8 @@ def load():
     L.snpgpu_normalize_newlines_dev.argtypes = [vp, vp, sz]
     L.snpgpu_reference_bases.restype = ctypes.c_int
     L.snpgpu_reference_bases.argtypes = [vp, vp, sz, vp, sz, vp, P(sz)]
+    L.snpgpu_pileup_want_vcf_records.restype = ctypes.c_int
+    L.snpgpu_pileup_want_vcf_records.argtypes = [vp, ctypes.c_int]
     L.snpgpu_pileup_vcf_records.restype = ctypes.c_int
     L.snpgpu_pileup_vcf_records.argtypes = [vp, vp, P(Params), ctypes.c_int, vp, sz, P(sz), vp, sz, P(sz)]
     L.snpgpu_merge_sites.restype = ctypes.c_int
@@ -341,6 +343,10 @@ class Context(object):
             raise IndexError("index out of range")             # what Bio.Seq / str indexing raises (utils.py:1108)
         self._check(rc)
         return out
+
+    def want_vcf_records(self, on=True):
+        """pileup_vcf_records() will follow the next pileup_consensus() calls: list the parsed lines on the way."""
+        self._check(self.lib.snpgpu_pileup_want_vcf_records(self.handle, 1 if on else 0))
 
     def pileup_vcf_records(self, sites, params, mode=MODE_SITES):
         """K5: the tallies behind the consensus VCF, one record per pileup line that the preceding pileup_consensus()

@@ -43,7 +43,12 @@ struct snpgpu_ctx {
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     size_t text_nbytes = 0;                   // bytes of the last text snpgpu_pileup_consensus() staged ...
     bool   text_valid = false;                // ... still there (snpgpu_pileup_vcf_records works on it)
+    bool   want_rec = false;                  // snpgpu_pileup_want_vcf_records: list the parsed lines during the call itself
+    bool   rec_valid = false;                 // the last snpgpu_pileup_consensus() left its line list in rec_off ...
+    size_t rec_listed = 0;                    // ... this many entries
+    int    rec_mode = 0;
     DevBuf rec_off, rec_sorted, rec_out, alt_out, k5_tmp, k5_state;
+    size_t rec_cap = 0;                       // entries of rec_off
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
     DevBuf synth_tmp, synth_n;
@@ -577,14 +582,33 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
         CK(ctx->stats.ensure(sizeof(snpgpu_pileup_stats)));
         if (want_lines) CK(ctx->lines.ensure(line_out_cap * sizeof(uint16_t)));
         if (nbytes && !skip_copy) CK(cudaMemcpyAsync(ctx->text.p, text, nbytes, cudaMemcpyHostToDevice, st));
-        int rc = snpgpu_pileup_consensus_dev(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p,
-                                             want_lines ? (uint16_t *)ctx->lines.p : nullptr, line_out_cap,
-                                             (snpgpu_pileup_stats *)ctx->stats.p);
+        // the consensus-VCF pass wants the list of parsed lines: in sites mode those are the lines at sites, which the
+        // follow-up kernel handles anyway -- listing them costs this run nothing, and K5 need not run K1 again
+        const bool list_now = ctx->want_rec && mode == SNPGPU_MODE_SITES;
+        ctx->rec_valid = false;
+        if (list_now) {
+            ctx->rec_cap = std::max(ctx->rec_cap, 4 * sites->n_unique + 1024);
+            CK(ctx->rec_off.ensure(ctx->rec_cap * sizeof(unsigned long long)));
+            CK(ctx->k5_state.ensure(256 + sizeof(PileupStatusDev)));
+            CK(cudaMemsetAsync(ctx->k5_state.p, 0, 256 + sizeof(PileupStatusDev), st));
+        }
+        int rc = k1_run(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p,
+                        want_lines ? (uint16_t *)ctx->lines.p : nullptr, line_out_cap, (snpgpu_pileup_stats *)ctx->stats.p,
+                        list_now ? (unsigned long long *)ctx->rec_off.p : nullptr,
+                        list_now ? (unsigned long long *)ctx->k5_state.p : nullptr, list_now ? ctx->rec_cap : 0);
         if (rc) return rc;
         snpgpu_pileup_stats hs;
+        unsigned long long listed = 0;
+        if (list_now) CK(cudaMemcpyAsync(&listed, ctx->k5_state.p, sizeof(listed), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&hs, ctx->stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
         if (sites->n_snp) CK(cudaMemcpyAsync(row_out, ctx->row.p, sites->n_snp, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (list_now && listed > ctx->rec_cap && attempt < 3) {   // the line list was too small: grow, redo
+            ctx->rec_cap = (size_t)listed + 1024;
+            skip_copy = true;
+            continue;
+        }
+        if (list_now) { ctx->rec_valid = true; ctx->rec_listed = (size_t)listed; ctx->rec_mode = mode; }
         if (hs.error_code == SNPGPU_E_LONECR && !normalized) {   // classic-Mac line ends: universal newlines, redo
             ctx->launches += (uint64_t)k1_launch_normalize(st, (uint8_t *)ctx->text.p, nbytes);
             normalized = true;
@@ -709,20 +733,25 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
     unsigned long long *counts = (unsigned long long *)ctx->k5_state.p;
     PileupStatusDev *k5st = (PileupStatusDev *)((uint8_t *)ctx->k5_state.p + 256);
     CK(ctx->row.ensure(sites->n_snp + 16));
-    // ---- which lines did K1 parse?  run it again with the list switched on (the list may have to grow once)
-    size_t guess = mode == SNPGPU_MODE_ALL ? nbytes / 8 + 16 : 4 * sites->n_unique + 1024;
+    // ---- which lines did K1 parse?  The list of the call itself when it was asked for (snpgpu_pileup_want_vcf_records,
+    //      sites mode); else K1 runs again with the list switched on (the list may have to grow once)
     unsigned long long listed = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        CK(ctx->rec_off.ensure(guess * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(ctx->k5_state.p, 0, 256 + sizeof(PileupStatusDev), st));
-        int rc = k1_run(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p, nullptr, 0, nullptr,
-                        (unsigned long long *)ctx->rec_off.p, counts, guess);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(&listed, counts, sizeof(listed), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (listed <= guess) break;
-        guess = (size_t)listed;
-        if (attempt == 1) return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: line list kept growing");
+    if (ctx->rec_valid && ctx->rec_mode == mode) {
+        listed = ctx->rec_listed;
+    } else {
+        size_t guess = mode == SNPGPU_MODE_ALL ? nbytes / 8 + 16 : 4 * sites->n_unique + 1024;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CK(ctx->rec_off.ensure(guess * sizeof(unsigned long long)));
+            CK(cudaMemsetAsync(ctx->k5_state.p, 0, 256 + sizeof(PileupStatusDev), st));
+            int rc = k1_run(ctx, ctx->text.p, nbytes, sites, params, mode, (uint8_t *)ctx->row.p, nullptr, 0, nullptr,
+                            (unsigned long long *)ctx->rec_off.p, counts, guess);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(&listed, counts, sizeof(listed), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (listed <= guess) break;
+            guess = (size_t)listed;
+            if (attempt == 1) return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: line list kept growing");
+        }
     }
     const size_t n = (size_t)listed;
     *n_rec = n;
@@ -771,6 +800,13 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
         return SNPGPU_OK;
     }
     return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: scratch kept growing");
+}
+
+int snpgpu_pileup_want_vcf_records(snpgpu_ctx *ctx, int on) {
+    if (!ctx) return SNPGPU_E_ARG;
+    ctx->want_rec = on != 0;
+    if (!on) ctx->rec_valid = false;
+    return SNPGPU_OK;
 }
 
 int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes) {

@@ -11,20 +11,37 @@
 
 namespace snpgpu {
 
-// one bit per site; flags / snp_unique: every key is a snplist entry and the list is already in snplist order
+// one bit per site; every key is a snplist entry and the list is already in snplist order
 __global__ void k3_set_bits_kernel(const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
-                                   const int64_t *max_pos, uint32_t *bits, uint8_t *flags, int32_t *snp_unique) {
+                                   const int64_t *max_pos, uint32_t *bits, uint8_t *flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    flags[i] = SITE_SNP;                                     // (unique-site indices are ranks in the bitmap: at most n of them)
+    if (i == n) return;
+    const unsigned long long k = keys[i];
+    const int c = (int)(k >> 32);
+    const int64_t p = (int64_t)(k & 0xffffffffull);
+    if (c < n_contigs && p <= max_pos[c]) {                  // (a key outside the caller's contig lengths gets no bit: no line can hit it)
+        const int64_t b = bit_base[c] + p;
+        atomicOr(&bits[b >> 5], 1u << (b & 31));
+    }
+}
+
+// snplist entry i -> its unique-site index = the rank of its bit (after the scan); a key that got no bit points at the
+// spare cell n, which nothing ever writes: its matrix column reads '-' like any position without a pileup line
+__global__ void k3_unique_kernel(const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
+                                 const int64_t *max_pos, const uint32_t *bits, const uint32_t *rank, int32_t *snp_unique) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = keys[i];
     const int c = (int)(k >> 32);
     const int64_t p = (int64_t)(k & 0xffffffffull);
-    flags[i] = SITE_SNP;
-    snp_unique[i] = (int32_t)i;
-    if (c < n_contigs && p <= max_pos[c]) {                  // (a key outside the caller's contig lengths: no line can hit it)
+    int32_t u = (int32_t)n;
+    if (c < n_contigs && p <= max_pos[c]) {
         const int64_t b = bit_base[c] + p;
-        atomicOr(&bits[b >> 5], 1u << (b & 31));
+        u = (int32_t)(rank[b >> 5] + (uint32_t)__popc(bits[b >> 5] & ((1u << (b & 31)) - 1u)));
     }
+    snp_unique[i] = u;
 }
 
 struct PopcOp {
@@ -57,13 +74,16 @@ int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int
     if (cudaMemsetAsync(bits, 0, n_words * sizeof(uint32_t), stream) != cudaSuccess) return -1;
     int launches = 0;
     if (n) {
-        k3_set_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, flags,
-                                                                          snp_unique);
+        k3_set_bits_kernel<<<(unsigned)((n + 256) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, flags);
         launches++;
     }
     cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(bits, PopcOp());
     if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, rank, (int64_t)n_words, stream) != cudaSuccess) return -1;
     k3_pack_words_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(bits, rank, n_words, words);
+    if (n) {
+        k3_unique_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, rank, snp_unique);
+        launches++;
+    }
     return launches + 3;
 }
 

@@ -92,12 +92,15 @@ class Reader(object):
             mode = _lib.MODE_ALL if self.chrom_position_set is None else _lib.MODE_SITES
             params = caller.params(self.min_base_quality)
             try:
+                ctx.want_vcf_records(vcf_writer is not None)     # (K1 then lists the lines it parses on the way)
                 row, stats = ctx.pileup_consensus(text, sites, params, mode)[:2]
                 if vcf_writer is not None:      # one VCF record per line the reader yields (call_consensus.py:161-184)
                     records, alts = ctx.pileup_vcf_records(sites, params, mode)
                     vcf_writer.write_records(text, records, alts, caller, failed_snp_gt)
             except _lib.SnpGpuError as e:
                 raise translate_error(e, self.file_path)
+            finally:
+                ctx.want_vcf_records(False)
         finally:
             owner.free()
             sites.close()

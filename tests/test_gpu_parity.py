@@ -118,6 +118,37 @@ def test_realistic_text(ctx, seed):
         assert st.n_general < st.n_lines * 0.02 + 5
 
 
+def test_fp64_threshold_edges(ctx):
+    """SURVEY section 7, "fp64 threshold compare": 100 * 0.55 = 55.00000000000001 in IEEE double, so 55 of 100 fails
+    VarFreq while 56 passes -- through the first tier's threshold tables ('.' / ',' lines: the reference base wins) and
+    through the exact tiers (a written-out allele wins); and the strand-bias product 25 * 0.28 = 7.000000000000001: 7
+    reads on the weaker strand fail StrBias, 8 pass."""
+    from snp_pipeline_b200 import _lib
+    assert 100 * 0.55 > 55 and 25 * 0.28 > 7
+    chrom = linegen.CHROM
+    q = "I" * 100
+    lines = [
+        "%s\t1\tA\t100\t%s\t%s" % (chrom, "G" * 30 + "g" * 25 + "." * 45, q),     # G 55 of 100: fails at 0.55 (exact tiers)
+        "%s\t2\tA\t100\t%s\t%s" % (chrom, "G" * 30 + "g" * 26 + "." * 44, q),     # G 56 of 100: passes
+        "%s\t3\tA\t100\t%s\t%s" % (chrom, "." * 30 + "," * 25 + "G" * 45, q),     # ref 55 of 100: fails (first tier's table)
+        "%s\t4\tA\t100\t%s\t%s" % (chrom, "." * 30 + "," * 26 + "G" * 44, q),     # ref 56 of 100: passes
+        "%s\t5\tC\t25\t%s\t%s" % (chrom, "." * 7 + "," * 18, "I" * 25),            # strand bias: 7 < 25 * 0.28
+        "%s\t6\tC\t26\t%s\t%s" % (chrom, "." * 8 + "," * 17 + "$", "I" * 25),      # 8 of 25: passes
+    ]
+    text = ("\n".join(lines) + "\n").encode()
+    snps = [(chrom, k) for k in range(1, 7)]
+    for ps in ((0, 0.55, 1, 0, 0.0), (0, 0.55, 1, 0, 0.28)):
+        for all_pos in (False, True):
+            _compare(ctx, text, snps, [], ps, all_pos)
+    sites = ctx.sites(snps)
+    row, _, per_line = ctx.pileup_consensus(text, sites, _lib.make_params(0, 0.55, 1, 0, 0.0), _lib.MODE_ALL, want_lines=True)
+    assert row == b"-G-A" + b"CC"
+    assert [int(v) >> 8 for v in per_line] == [_lib.FAIL_VARFREQ, 0, _lib.FAIL_VARFREQ, 0, 0, 0]
+    row, _, per_line = ctx.pileup_consensus(text, sites, _lib.make_params(0, 0.5, 1, 0, 0.28), _lib.MODE_ALL, want_lines=True)
+    assert [int(v) >> 8 for v in per_line][4:] == [_lib.FAIL_STRBIAS, 0] and row[4:] == b"-C"
+    sites.close()
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_indel_token_corners(ctx, seed):
     """Well- and ill-formed indel tokens at every alignment against the column's end (tests/linegen.py): the lines the
@@ -461,6 +492,17 @@ def test_site_table_built_on_device(ctx):
             if mode == _lib.MODE_ALL:
                 assert np.array_equal(got[2], want[2])
     host.close()
+    # keys beyond the contig lengths the caller gave (and on a contig it did not name) get no bit: their columns read '-'
+    # and every site behind them still lands in its own column
+    extra = sorted(snps + [(0, 3500), (0, 9000), (1, 1201), (1, 70000), (2, 5)])
+    keys2 = np.array([(c << 32) | q for c, q in extra], dtype=np.uint64)
+    keys2_dev = torch.from_numpy(keys2.view(np.int64)).cuda()
+    dev = _lib.Sites.from_keys_dev(ctx, contigs, lens, keys2_dev.data_ptr(), keys2.size)
+    got = ctx.pileup_consensus(text, dev, p, _lib.MODE_SITES)[0]
+    dev.close()
+    ref_row = dict(zip(snps, ctx.pileup_consensus(text, _lib.Sites.from_arrays(
+        ctx, contigs, np.array([c for c, _ in snps], np.int32), np.array([q for _, q in snps], np.int64)), p, _lib.MODE_SITES)[0]))
+    assert bytes(ref_row.get(k, ord("-")) for k in extra) == got
     empty = _lib.Sites.from_keys_dev(ctx, contigs, lens, 0, 0)
     row, stats = ctx.pileup_consensus(text, empty, p, _lib.MODE_SITES)[:2]
     assert row == b"" and stats.n_parsed == 0
