@@ -292,6 +292,47 @@ def cpu_baseline(w, matrix_host, n_samples):
             "k1_positions_per_s_per_core": n_samples * w.args.genome_len / t_k1}, d
 
 
+def reference_python_leg(w, n_lines=150_000):
+    """The reference's OWN Python (staged under oracle/_ref by oracle/stage_ref.py, unmodified) on the first n_lines of
+    one synthetic sample: pileup.Reader over every line + ConsensusCaller.call_consensus per record, one core -- the loop
+    of call_consensus.py:161-176 without the file writing.  None when the modules are not staged."""
+    import tempfile
+    from oracle import stage_ref
+    root = stage_ref.staged_root()
+    if root is None:
+        return None
+    os.environ["SNP_REFERENCE_ROOT"] = root
+    from oracle import ref_harness
+    ref_harness.REFERENCE_ROOT = root
+    try:
+        pileup = ref_harness.ref("pileup")
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+    text = w.texts[0][:w.nbytes[0]].cpu().numpy().tobytes()
+    end, k = 0, 0
+    while k < n_lines:
+        nxt = text.find(b"\n", end)
+        if nxt < 0:
+            break
+        end, k = nxt + 1, k + 1
+    with tempfile.NamedTemporaryFile("wb", suffix=".pileup", delete=False) as f:
+        f.write(text[:end])
+        path = f.name
+    try:
+        caller = pileup.ConsensusCaller(0.6, 3, 0, 0.0)
+        t0 = time.perf_counter()
+        n = 0
+        for record in pileup.Reader(path, 0, None):
+            caller.call_consensus(record)
+            n += 1
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(path)
+    return {"positions_per_s_per_core": n / dt, "cores": 1, "lines_timed": n, "seconds": dt,
+            "what": "snppipeline/pileup.py (unmodified, staged by oracle/stage_ref.py): Reader(all positions) + "
+                    "ConsensusCaller.call_consensus per record"}
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU restatement of the reference's path with every host thread, bounded sample."""
     if rank != 0:
@@ -781,6 +822,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, d_cpu = cpu_baseline(w, matrix_host, min(args.cpu_samples, w.n))
         assert np.array_equal(d_cpu, d_host), "cpu_baseline: the oracle's distance matrix differs from the GPU's"
+        cpu["reference_python"] = reference_python_leg(w)
 
     if rank == 0:
         line = {

@@ -449,7 +449,10 @@ static int k1_run_batch(snpgpu_ctx *ctx, const snpgpu_pileup_sample *smp, size_t
     const size_t z_total = z_head + n * z_per;
     CK(ctx->k1_zero.ensure(z_total));
     CK(ctx->arena.ensure(ctx->arena_want));
-    const size_t q_cap = std::max<size_t>(ctx->queue_want, has_qual ? total_bytes / 8 + 65536 : total_bytes / 512 + 65536);
+    // follow-up queue: a share of the lines (all of them with a minimum base quality) + the blocks of 64 slots every warp
+    // of the grid may hold half filled (k1_pileup.cu claims slots K1_QBLOCK at a time)
+    const size_t q_blocks = (size_t)ctx->n_sms * ctx->k1_blocks * K1_WARPS * 64 * 2;
+    const size_t q_cap = std::max<size_t>(ctx->queue_want, (has_qual || rec_off ? total_bytes / 8 : total_bytes / 256) + 65536 + q_blocks);
     CK(ctx->queue.ensure(q_cap * 16));
     if (want_lines) {
         CK(ctx->tile_first.ensure(stage_tiles * sizeof(unsigned long long)));
