@@ -221,6 +221,16 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
                               snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec,
                               snpgpu_vcf_alt *alt_out, size_t alt_cap, size_t *n_alt);
 
+/* ---- K6: the pileup by-product of collect_metrics.  Replaces the loop of collect_metrics.py:322-329: the sum over all
+ *      lines of int(line.split()[3]) -- the raw-depth column -- where lines without a fourth token or with one that is
+ *      no integer add nothing; the caller divides by the reference length and prints "%.2f" (collect_metrics.py:333-338).
+ *      lines_out (nullable): how many lines contributed.  SNPGPU_E_DOMAIN (a byte >= 0x80, an integer beyond int64):
+ *      *error_offset = byte offset of the first such line. ------------------------------------------------------- */
+int snpgpu_pileup_depth_sum(snpgpu_ctx *ctx, const void *text, size_t nbytes, int64_t *sum_out, uint64_t *lines_out,
+                            uint64_t *error_offset);
+int snpgpu_pileup_depth_sum_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, int64_t *sum_out, uint64_t *lines_out,
+                                uint64_t *error_offset /* host; synchronises */);
+
 /* Rewrites every CR that is not followed by LF to LF, in place (byte offsets and line structure under
  * universal newlines are unchanged).  Needed only after SNPGPU_E_LONECR. */
 int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes);

@@ -88,6 +88,8 @@ def lib():
         L.oracle_distance_rows.restype = None
         L.oracle_distance_rows.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p, ctypes.c_size_t,
                                            ctypes.c_size_t]
+        L.oracle_depth_sum.restype = ctypes.c_int
+        L.oracle_depth_sum.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64), u64p, u64p]
         L.oracle_distance_rows_strided.restype = None
         L.oracle_distance_rows_strided.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, i32p, ctypes.c_size_t,
                                                    ctypes.c_size_t, ctypes.c_size_t]
@@ -430,6 +432,23 @@ def hot_path_texts(names, texts, site_lists, params, parse_all=False, threads=1,
     for i, a in enumerate(ids):
         mat.append("%s\t%s\n" % (a, "\t".join(map(str, d[i].tolist()))))
     return snplist, snpma, "".join(mat), rows
+
+
+def depth_sum(text: bytes):
+    """collect_metrics.py:322-329: (sum of int(line.split()[3]) over the lines, lines that contributed)."""
+    total, lines, off = ctypes.c_int64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = lib().oracle_depth_sum(bytes(text), len(text), ctypes.byref(total), ctypes.byref(lines), ctypes.byref(off))
+    if rc:
+        raise OracleError(rc, off.value)
+    return total.value, lines.value
+
+
+def mean_pileup_depth_text(text: bytes, reference_length: int) -> str:
+    """collect_metrics.py:333-338: "%.2f" of depth_sum / reference_length, "" when either is not positive."""
+    total, _ = depth_sum(text)
+    if total > 0 and reference_length > 0:
+        return "%.2f" % (float(total) / float(reference_length))
+    return ""
 
 
 def distance_texts(seqs):

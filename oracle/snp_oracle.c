@@ -434,3 +434,52 @@ void oracle_distance_rows(const uint8_t *matrix, size_t n_rows, size_t n_sites, 
 void oracle_distance(const uint8_t *matrix, size_t n_rows, size_t n_sites, int32_t *dist_out) {
     oracle_distance_rows(matrix, n_rows, n_sites, dist_out, 0, n_rows);
 }
+
+/* ---- collect_metrics.py:322-329: depth_sum += int(line.split()[3]) over the lines of the pileup file (ValueError /
+ * IndexError ignored).  Lines end at '\n', '\r' or "\r\n" (Python's universal newlines); returns ORACLE_OK or
+ * ORACLE_E_DOMAIN (a byte >= 0x80, an integer beyond int64) with *error_offset = the offset of that line. */
+static int dsum_space(unsigned c) { return c == 0x20u || (c - 9u) < 5u || (c - 0x1cu) < 4u; }
+int oracle_depth_sum(const uint8_t *text, size_t n, int64_t *sum_out, uint64_t *lines_out, uint64_t *error_offset) {
+    int64_t sum = 0;
+    uint64_t lines = 0;
+    size_t s = 0;
+    *error_offset = ~(uint64_t)0;
+    while (s < n) {
+        size_t e = s;
+        while (e < n && text[e] != '\n' && text[e] != '\r') e++;
+        for (size_t k = s; k < e; k++)
+            if (text[k] >= 0x80u) { *error_offset = s; return ORACLE_E_DOMAIN; }
+        size_t i = s;
+        int tok = 0;
+        while (i < e) {
+            while (i < e && dsum_space(text[i])) i++;
+            if (i >= e) break;
+            size_t b = i;
+            while (i < e && !dsum_space(text[i])) i++;
+            if (++tok == 4) {
+                /* Python int(): optional sign, digits, single underscores between digits */
+                size_t j = b;
+                int neg = 0, ok = 1, prev_digit = 0;
+                uint64_t v = 0;
+                if (text[j] == '+' || text[j] == '-') { neg = text[j] == '-'; j++; }
+                if (j >= i) ok = 0;
+                for (; ok && j < i; j++) {
+                    unsigned c = text[j];
+                    if (c >= '0' && c <= '9') {
+                        if (v > (0x7fffffffffffffffULL - (c - '0')) / 10) { *error_offset = s; return ORACLE_E_DOMAIN; }
+                        v = v * 10 + (c - '0');
+                        prev_digit = 1;
+                    } else if (c == '_' && prev_digit && j + 1 < i && text[j + 1] >= '0' && text[j + 1] <= '9') {
+                        prev_digit = 0;
+                    } else ok = 0;
+                }
+                if (ok) { sum += neg ? -(int64_t)v : (int64_t)v; lines++; }
+                break;
+            }
+        }
+        s = e + 1;                      /* ("\r\n": the empty line between the two adds nothing) */
+    }
+    *sum_out = sum;
+    *lines_out = lines;
+    return ORACLE_OK;
+}

@@ -27,7 +27,7 @@ EXPORTS = [
     "snpgpu_normalize_newlines_dev", "snpgpu_pileup_vcf_records", "snpgpu_pileup_want_vcf_records", "snpgpu_reference_bases",
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_pairwise_distance_tiles_dev",
-    "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites",
+    "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites", "snpgpu_pileup_depth_sum", "snpgpu_pileup_depth_sum_dev",
 ]
 
 
@@ -153,6 +153,10 @@ def load():
     L.snpgpu_pairwise_distance_dev.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp]
     L.snpgpu_pairwise_distance_tiles_dev.restype = ctypes.c_int
     L.snpgpu_pairwise_distance_tiles_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp]
+    L.snpgpu_pileup_depth_sum.restype = ctypes.c_int
+    L.snpgpu_pileup_depth_sum.argtypes = [vp, vp, sz, P(ctypes.c_int64), P(u64), P(u64)]
+    L.snpgpu_pileup_depth_sum_dev.restype = ctypes.c_int
+    L.snpgpu_pileup_depth_sum_dev.argtypes = [vp, vp, sz, P(ctypes.c_int64), P(u64), P(u64)]
     L.snpgpu_synth_pileup_dev.restype = ctypes.c_int
     L.snpgpu_synth_pileup_dev.argtypes = [vp, P(SynthSpec), ctypes.c_char_p, vp, sz, P(sz)]
     L.snpgpu_synth_sample_sites.restype = ctypes.c_int
@@ -403,6 +407,17 @@ class Context(object):
                 arr[k] = PileupSample(tp or None, int(nb), rp or None, lp or None, int(lc), sp or None)
         self._check(self.lib.snpgpu_pileup_consensus_batch_dev(self.handle, arr, len(arr), sites.handle,
                                                                ctypes.byref(params), mode))
+
+    # -- K6 ---------------------------------------------------------------------------------------
+    def pileup_depth_sum(self, text):
+        """(sum of the raw-depth column over all lines, lines that contributed): collect_metrics.py:322-329.
+        text: bytes-like / uint8 ndarray with the pileup file's contents."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+        total, lines, off = ctypes.c_int64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        rc = self.lib.snpgpu_pileup_depth_sum(self.handle, _np_ptr(buf), buf.size, ctypes.byref(total), ctypes.byref(lines),
+                                              ctypes.byref(off))
+        self._check(rc, off.value)
+        return total.value, lines.value
 
     # -- K2 ---------------------------------------------------------------------------------------
     def merge_sites(self, keys, sample_of):

@@ -812,6 +812,41 @@ int snpgpu_pileup_want_vcf_records(snpgpu_ctx *ctx, int on) {
     return SNPGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------ K6
+int snpgpu_pileup_depth_sum_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, int64_t *sum_out, uint64_t *lines_out,
+                                uint64_t *error_offset) {
+    if (!ctx || (nbytes && !text_dev) || !sum_out) return fail(ctx, SNPGPU_E_ARG, "pileup_depth_sum: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->k5_state.ensure(256 + sizeof(PileupStatusDev)));
+    unsigned long long *out3 = (unsigned long long *)ctx->k5_state.p;
+    const int launched = k6_launch_depth_sum(ctx->stream, (const uint8_t *)text_dev, nbytes, out3);
+    if (launched < 0) return fail(ctx, SNPGPU_E_CUDA, "pileup_depth_sum: launch failed");
+    ctx->launches += (uint64_t)launched;
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, out3, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    *sum_out = (int64_t)h[0];
+    if (lines_out) *lines_out = h[1];
+    if (error_offset) *error_offset = ~0ull;
+    if (h[2]) {
+        const unsigned long long e = ~h[2];
+        if (error_offset) *error_offset = e >> 8;
+        return fail(ctx, (int)(e & 0xff), "pileup_depth_sum: a line outside the byte / int64 domain");
+    }
+    return SNPGPU_OK;
+}
+
+int snpgpu_pileup_depth_sum(snpgpu_ctx *ctx, const void *text, size_t nbytes, int64_t *sum_out, uint64_t *lines_out,
+                            uint64_t *error_offset) {
+    if (!ctx || (nbytes && !text) || !sum_out) return fail(ctx, SNPGPU_E_ARG, "pileup_depth_sum: null argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->text_valid = false;
+    CK(ctx->text.ensure(nbytes + 64));
+    if (nbytes) CK(cudaMemcpyAsync(ctx->text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return snpgpu_pileup_depth_sum_dev(ctx, ctx->text.p, nbytes, sum_out, lines_out, error_offset);
+}
+
 int snpgpu_normalize_newlines_dev(snpgpu_ctx *ctx, void *text_dev, size_t nbytes) {
     if (!ctx || (nbytes && !text_dev)) return fail(ctx, SNPGPU_E_ARG, "normalize_newlines: null argument");
     CK(cudaSetDevice(ctx->device));

@@ -20,6 +20,9 @@ int    k5_launch_tally(cudaStream_t stream, const uint8_t *text, size_t nbytes, 
                        const unsigned long long *offsets, size_t n_rec, snpgpu_vcf_record *rec_out, snpgpu_vcf_alt *alt_out,
                        size_t alt_cap, unsigned long long *alt_count, PileupStatusDev *st, uint8_t *arena, size_t arena_cap);
 
+// k6_metrics.cu
+int    k6_launch_depth_sum(cudaStream_t stream, const uint8_t *text, size_t nbytes, unsigned long long *out3);
+
 // k3_sites.cu
 size_t k3_scan_bytes(size_t n_words);
 int    k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
