@@ -140,7 +140,7 @@ class Workload(object):
         self.cnt_dev = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
         self.sout_dev = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
         self.lines_dev = torch.empty((self.n, args.genome_len + 64), dtype=torch.int16, device="cuda")
-        self.stats_dev = torch.zeros((self.n, 5), dtype=torch.int64, device="cuda")
+        self.stats_dev = torch.zeros((self.n, 6), dtype=torch.int64, device="cuda")
         self.params = _lib.make_params(min_cons_depth=3)
 
     def spec(self, i):

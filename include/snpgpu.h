@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SNPGPU_ABI_VERSION 1
+#define SNPGPU_ABI_VERSION 2
 
 /* ---- status codes ----------------------------------------------------------------------------- */
 #define SNPGPU_OK            0
@@ -134,6 +134,7 @@ typedef struct {
     uint64_t error_offset;   /* byte offset of the first raising line, or UINT64_MAX    */
     int32_t  error_code;
     int32_t  reserved;
+    uint64_t n_called;       /* snplist positions that received a call: call_consensus.py:184's "called consensus positions" */
 } snpgpu_pileup_stats;
 
 /* text in host memory (pinned or pageable); copies are streamed inside the call */

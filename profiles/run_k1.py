@@ -28,7 +28,7 @@ sites = _lib.Sites.from_arrays(ctx, ["gi|0000000|ref|SYN_5000K.1|"], np.zeros(po
 B = int(os.environ.get("BATCH", "8"))                     # samples per launch (the same text, separate outputs)
 row = torch.empty((B, max(pos.size, 1)), dtype=torch.uint8, device="cuda")
 lines = torch.empty((B, G + 64), dtype=torch.int16, device="cuda")
-stats = torch.zeros((B, 5), dtype=torch.int64, device="cuda")
+stats = torch.zeros((B, 6), dtype=torch.int64, device="cuda")
 p = _lib.make_params(min_cons_depth=3)
 ctx.enable_timing(True)
 batch = [(buf.data_ptr(), n, row[i].data_ptr(), lines[i].data_ptr(), G + 64, stats[i].data_ptr()) for i in range(B)]

@@ -40,7 +40,8 @@ class Params(ctypes.Structure):
 
 class PileupStats(ctypes.Structure):
     _fields_ = [("n_lines", ctypes.c_uint64), ("n_parsed", ctypes.c_uint64), ("n_general", ctypes.c_uint64),
-                ("error_offset", ctypes.c_uint64), ("error_code", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("error_offset", ctypes.c_uint64), ("error_code", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_called", ctypes.c_uint64)]
 
 
 class PileupSample(ctypes.Structure):
@@ -254,7 +255,7 @@ class Context(object):
 
     def __init__(self, device=0):
         self.lib = load()
-        if self.lib.snpgpu_abi_version() != 1:
+        if self.lib.snpgpu_abi_version() != 2:
             raise SnpGpuError(E_ARG, "libsnpgpu ABI mismatch")
         h = ctypes.c_void_p()
         rc = self.lib.snpgpu_create(int(device), ctypes.byref(h))

@@ -36,7 +36,7 @@ class HotPathResult(object):
         self.sample_names = []        # all samples, matrix row order
         self.matrix = None            # torch uint8 [n_samples, n_sites] (every rank, after the row all-gather)
         self.distance = None          # torch int32 [n_samples, n_samples] on rank 0, else None
-        self.stats = None             # numpy int64 [n_local, 5]: n_lines, n_parsed, n_general, error_offset, error_code
+        self.stats = None             # numpy int64 [n_local, 6]: n_lines, n_parsed, n_general, error_offset, error_code, n_called
         self.files = {}
 
 
@@ -177,7 +177,7 @@ def run_hot_path(ctx, local_names, local_texts, local_sites, contigs, contig_len
     sites = _lib.Sites.from_keys_dev(ctx, chroms, [len_of[c] for c in chroms], uniq.data_ptr(), n_sites)
     width = (max(n_sites, 1) + 63) // 64 * 64                # row stride: 16-byte aligned rows (K4's coalesced pack kernel)
     block = torch.full((per, width), ord("-"), dtype=torch.uint8, device=dev)
-    stats = torch.zeros((max(n_local, 1), 5), dtype=torch.int64, device=dev)
+    stats = torch.zeros((max(n_local, 1), 6), dtype=torch.int64, device=dev)
     if n_local:
         ctx.pileup_consensus_batch_dev([(t.data_ptr(), int(t.numel()), block[i].data_ptr(), 0, 0, stats[i].data_ptr())
                                         for i, t in enumerate(local_texts)], sites, params, mode)

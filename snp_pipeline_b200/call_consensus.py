@@ -74,6 +74,9 @@ def call_consensus(args):
     finally:
         if writer:
             writer.close()
+    # call_consensus.py:184 counts the entries of its position -> base dict: the snplist positions that received a call
+    # (a position the pileup never reaches, or one whose lines all were overwritten by '-', still counts when called)
+    utils.verbose_print("called consensus positions = %i" % stats.n_called)
     utils.verbose_print("parsed pileup lines = %i of %i" % (stats.n_parsed, stats.n_lines))
 
     with open(consensus_file_path, "w") as fasta_file_object:

@@ -84,7 +84,7 @@ def parse_argument_list(argv):
     sp.add_argument("-b", "--minConsStrdBias", dest="minConsStrdBias", type=_min_cons_strand_bias, default=0,
                     metavar="FREQ", help="Strand bias. Minimum fraction of consensus-supporting reads on each strand.")
     sp.add_argument("--vcfFileName", dest="vcfFileName", type=str, default=None, metavar="NAME",
-                    help="VCF Output file name (not produced by this build yet; a warning is printed).")
+                    help="VCF Output file name.  If not set, no VCF file is written.")
     sp.add_argument("--vcfRefName", dest="vcfRefName", type=str, default="Unknown reference", metavar="NAME",
                     help="Name of the reference file.  Only used in the generated VCF file header.")
     sp.add_argument("--vcfAllPos", dest="vcfAllPos", action="store_true",

@@ -489,6 +489,7 @@ static int k1_run_batch(snpgpu_ctx *ctx, const snpgpu_pileup_sample *smp, size_t
         }
         S.rec_off = rec_off; S.rec_count = rec_count; S.rec_cap = rec_cap;
         S.row_out = smp[i].row_out_dev;
+        S.n_unique = sites->n_unique;
         S.stats_out = smp[i].stats_dev;
     }
     g.n_samples = (int)n;
@@ -766,8 +767,7 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
     CK(ctx->rec_sorted.ensure(n * sizeof(unsigned long long)));
     if (k5_sort_offsets(st, (const unsigned long long *)ctx->rec_off.p, (unsigned long long *)ctx->rec_sorted.p, n,
                         ctx->k5_tmp.p, ctx->k5_tmp.cap))
-        return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: sort failed");
-    ctx->launches += 4;
+        return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: sort failed");      // (CUB's kernels: not counted among the library's own launches)
     // ---- tallies; ALT entries are claimed with a counter, so the device buffer may have to grow once as well
     CK(ctx->rec_out.ensure(n * sizeof(snpgpu_vcf_record)));
     size_t alt_room = std::max<size_t>(alt_cap, 2 * n + 64);

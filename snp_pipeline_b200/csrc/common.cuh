@@ -21,6 +21,8 @@ struct PileupStatusDev {
     unsigned int       arena_overflow;
     unsigned int       next_tile;     // the pileup kernel's tile tickets (warps take tiles in increasing order)
     unsigned long long over_used;     // entries claimed in the per-line results' overflow list
+    unsigned long long n_called;      // snplist positions that received a call (the finish kernel counts them) ...
+    unsigned int       finish_done;   // ... its blocks that are through: the last one writes the caller's stats
 };
 
 // ---- geometry of the pileup kernel (k1_pileup.cu): every warp is its own pipeline --------------
@@ -86,6 +88,7 @@ struct K1Samp {
     unsigned long long *rec_count;
     unsigned long long  rec_cap;
     uint8_t            *row_out;       // n_snp bytes, snplist order
+    unsigned long long  n_unique;      // unique sites of the table
     snpgpu_pileup_stats *stats_out;    // nullable
 };
 

@@ -476,30 +476,41 @@ __global__ void k1_finish_kernel(const __grid_constant__ K1Batch g) {
         const unsigned long long c = S.site_cells[g.snp_unique[k]];
         S.row_out[k] = c ? (uint8_t)(c & 0xffu) : (uint8_t)'-';
     }
-    if (k == 0 && S.stats_out) {
-        const PileupStatusDev *st = S.st, *ast = g.s[0].st;
-        snpgpu_pileup_stats *out = S.stats_out;
-        out->n_lines = st->n_lines;
-        out->n_parsed = st->n_parsed;
-        out->n_general = st->n_general;
-        out->reserved = 0;
-        const unsigned long long queued = *g.queue_count;
-        if (queued > g.queue_cap) {                           // the follow-up queue was too small: entries the batch needs
-            out->error_offset = queued;
-            out->reserved = -1;
-            out->error_code = SNPGPU_E_NOMEM;
-        } else if (ast->arena_overflow || st->over_used > g.over_cap) {
-            out->error_offset = ast->arena_overflow ? ast->arena_used : 0ull;    // bytes of splice scratch the batch needs
-            out->reserved = st->over_used > g.over_cap ? (int32_t)((st->over_used + 1023ull) >> 10) : 0;   // overflow entries / 1024
-            out->error_code = SNPGPU_E_NOMEM;
-        } else if (st->first_error_inv != 0ull) {
-            const unsigned long long e = ~st->first_error_inv;
-            out->error_offset = e >> 8;
-            out->error_code = (int32_t)(e & 0xffull);
-        } else {
-            out->error_offset = ~0ull;
-            out->error_code = 0;
-        }
+    if (!S.stats_out) return;
+    // "called consensus positions" (call_consensus.py:184): the snplist positions at least one parsed line fell on
+    unsigned called = 0;
+    for (size_t u = k; u < S.n_unique; u += (size_t)gridDim.x * blockDim.x)
+        called += ((g.sites.flags[u] & SITE_SNP) && S.site_cells[u] != 0ull) ? 1u : 0u;
+    called = __reduce_add_sync(0xffffffffu, called);
+    if ((threadIdx.x & 31u) == 0u && called) atomicAdd(&S.st->n_called, (unsigned long long)called);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence();
+    if (atomicAdd(&S.st->finish_done, 1u) != gridDim.x - 1u) return;      // (the sample's last block writes the stats)
+    __threadfence();
+    const volatile PileupStatusDev *st = S.st, *ast = g.s[0].st;
+    snpgpu_pileup_stats *out = S.stats_out;
+    out->n_lines = st->n_lines;
+    out->n_parsed = st->n_parsed;
+    out->n_general = st->n_general;
+    out->n_called = st->n_called;
+    out->reserved = 0;
+    const unsigned long long queued = *g.queue_count;
+    if (queued > g.queue_cap) {                               // the follow-up queue was too small: entries the batch needs
+        out->error_offset = queued;
+        out->reserved = -1;
+        out->error_code = SNPGPU_E_NOMEM;
+    } else if (ast->arena_overflow || st->over_used > g.over_cap) {
+        out->error_offset = ast->arena_overflow ? ast->arena_used : 0ull;        // bytes of splice scratch the batch needs
+        out->reserved = st->over_used > g.over_cap ? (int32_t)((st->over_used + 1023ull) >> 10) : 0;   // overflow entries / 1024
+        out->error_code = SNPGPU_E_NOMEM;
+    } else if (st->first_error_inv != 0ull) {
+        const unsigned long long e = ~st->first_error_inv;
+        out->error_offset = e >> 8;
+        out->error_code = (int32_t)(e & 0xffull);
+    } else {
+        out->error_offset = ~0ull;
+        out->error_code = 0;
     }
 }
 

@@ -52,7 +52,7 @@ int k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *sample_
     if (cub::DeviceRunLengthEncode::Encode(cub_tmp, rb, sorted, uniq_out, count_out, n_uniq_dev, (int64_t)n, stream) !=
         cudaSuccess)
         return SNPGPU_E_CUDA;
-    *launches += 10;   // histogram + up to 8 onesweep passes + run-length encode (CUB-internal; an upper estimate)
+    *launches += 0;    // (the sort and the run-length encode are CUB's kernels: not counted among this library's own launches)
     return 0;
 }
 

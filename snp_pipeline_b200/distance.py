@@ -32,10 +32,8 @@ def distance_matrix(seqs, ids):
     Unequal lengths follow the reference's loop `for i in range(len(seq1))` over sorted pairs: a later, shorter
     sequence raises IndexError; a later, longer one is compared over the shorter prefix (padding with '-')."""
     lens = [len(seqs[i]) for i in ids]
-    for a in range(len(ids)):
-        for b in range(a + 1, len(ids)):
-            if lens[b] < lens[a]:
-                raise IndexError("string index out of range")
+    if any(lens[k + 1] < lens[k] for k in range(len(lens) - 1)):     # (some later sequence is shorter than an earlier one)
+        raise IndexError("string index out of range")
     width = max(lens) if lens else 0
     m = np.full((len(ids), max(width, 1)), ord("-"), dtype=np.uint8)
     for r, i in enumerate(ids):

@@ -71,8 +71,8 @@ def merged_snplist_text(names, per_sample):
     rank = {c: i for i, c in enumerate(chroms)}
     for s in per_sample:
         for _, p in s:
-            if not 0 <= p < (1 << 32):
-                raise ValueError("VCF position %d outside [0, 2^32)" % p)
+            if not 0 <= p < (1 << 31):                 # (the site table's range: call_consensus accepts what this step writes)
+                raise ValueError("VCF position %d outside [0, 2^31)" % p)
     keys = np.array([(rank[c] << 32) | p for s in per_sample for c, p in s], dtype=np.uint64)
     samp = np.array([i for i, s in enumerate(per_sample) for _ in s], dtype=np.uint32)
     uniq, cnt, samples = device.context().merge_sites(keys, samp)

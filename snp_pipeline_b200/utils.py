@@ -168,7 +168,6 @@ def _file_problem(message, error_handler, continue_possible):
     elif error_handler == "sample":
         sample_error(message, continue_possible)
     else:
-        _err_log([message]) if False else None
         print(message, file=sys.stderr)
         path = os.environ.get("errorOutputFile")
         if path:

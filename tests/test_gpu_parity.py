@@ -53,7 +53,7 @@ def _compare(ctx, text, snps, excl, ps, all_pos):
     op = orc.make_params(*ps)
     want_err = 0
     try:
-        want_row, (cells, fails, _) = orc.pileup_consensus(text, snps, excl, op, parse_all=all_pos, want_lines=True)
+        want_row, (cells, fails, poss) = orc.pileup_consensus(text, snps, excl, op, parse_all=all_pos, want_lines=True)
     except orc.OracleError as e:
         want_err, err_line = e.status, e.line
     sites = ctx.sites(snps, excl)
@@ -69,6 +69,14 @@ def _compare(ctx, text, snps, excl, ps, all_pos):
         row, stats = out[0], out[1]
         assert row == want_row
         assert stats.n_lines == len(_line_offsets(text))
+        # call_consensus.py:184 "called consensus positions": snplist positions that got at least one parsed line
+        chroms = {c for c, _ in snps}
+        assert stats.n_called <= len(set(snps))
+        if len(chroms) == 1:
+            c0 = next(iter(chroms)).encode()
+            body = [ln for ln in text.replace(b"\r\n", b"\n").replace(b"\r", b"\n").split(b"\n") if ln.strip()]
+            if all(ln.split()[0] == c0 for ln in body):
+                assert stats.n_called == len({int(q) for q in poss} & {q for _, q in snps})
         if all_pos:
             lines = out[2]
             assert len(lines) == len(cells)
@@ -330,7 +338,7 @@ def test_synthetic_sample_device_resident(ctx, genome_len, sample):
     p = _lib.make_params(min_cons_depth=3)
     row = torch.empty(len(snps), dtype=torch.uint8, device="cuda")
     lines = torch.empty(genome_len + 8, dtype=torch.int16, device="cuda")
-    stats = torch.zeros(5, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(6, dtype=torch.int64, device="cuda")
     text = buf[:n].cpu().numpy()
     op = orc.make_params(min_cons_depth=3)
     want_row, (cells, fails, _) = orc.pileup_consensus(text, snps, [], op, parse_all=True, want_lines=True)
@@ -379,7 +387,7 @@ def test_batch_of_samples_one_launch(ctx, mode_all):
     rows = torch.zeros((B, len(snps)), dtype=torch.uint8, device="cuda")
     cap = max(lens) + 8
     lines = torch.zeros((B, cap), dtype=torch.int16, device="cuda")
-    stats = torch.zeros((B, 5), dtype=torch.int64, device="cuda")
+    stats = torch.zeros((B, 6), dtype=torch.int64, device="cuda")
     mode = _lib.MODE_ALL if mode_all else _lib.MODE_SITES
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.pileup_consensus_batch_dev([(bufs[i].data_ptr(), ns[i], rows[i].data_ptr(), lines[i].data_ptr() if mode_all else 0,

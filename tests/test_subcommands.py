@@ -74,7 +74,7 @@ def test_abi_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(L, n)]
     assert not missing, missing
     assert set(_lib.EXPORTS) <= declared
-    assert L.snpgpu_abi_version() == 1
+    assert L.snpgpu_abi_version() == 2
 
 
 def test_no_cpu_fallback():
