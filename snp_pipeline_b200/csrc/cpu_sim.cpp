@@ -9,14 +9,12 @@
 #include <string.h>
 #include <vector>
 #include "line_fast.cuh"
-#include "line_quick.cuh"
 #include "line_quick3.cuh"
 #include "line_general.cuh"
 #include "sites_host.h"
 
 using namespace snpgpu;
 
-static int g_variant = 1;      // 0: line_quick.cuh (the round-1 first tier, kept as a second opinion), 1: line_quick3.cuh (k1_pileup.cu)
 
 struct HostWin {                // line_quick3.cuh's memory policy over a plain array: window words, then the name rows
     const uint32_t *p;
@@ -29,8 +27,6 @@ struct HostWin {                // line_quick3.cuh's memory policy over a plain 
 };
 
 extern "C" {
-
-void cpusim_set_variant(int v) { g_variant = v; }
 
 // counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code,
 // [5] = lines decided by the first-tier parser
@@ -61,9 +57,6 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         if (buf[i] == '\r' && buf[i + 1] != '\n') buf[i] = '\n';
     uint64_t n_lines = 0, n_parsed = 0, n_general = 0, n_quick = 0;
     int hint = 0;
-    alignas(16) uint32_t cc_name[16], cc_mask[16];
-    ContigCache cc;
-    contig_cache_load(t, hint, cc_name, cc_mask, 16, &cc);
     size_t s = 0;
     counters[3] = ~0ull; counters[4] = 0;
     std::vector<uint8_t> scratch;
@@ -78,12 +71,9 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         const size_t line_idx = n_lines++;
         int st = ST_FALLBACK;
         FastLine fl;
-        if (!force_general && (!high || g_variant == 1) && p->min_base_qual <= 0) {   // first tier (k1_stream.cu has no tile-wide byte check)
-            QuickLine q;
-            if (cc.cid != hint) contig_cache_load(t, hint, cc_name, cc_mask, 16, &cc);    // the kernel reloads after a drain
-            if (g_variant == 0) {
-                st = quick_line(buf, (uint32_t)s, (uint32_t)nbytes, t, cc, *p, all_positions != 0, &q);
-            } else {                                                     // the steps of k1_pileup.cu's lane loop
+        if (!force_general && p->min_base_qual <= 0) {                   // first tier: the steps of k1_pileup.cu's lane loop
+            struct { int32_t site; uint32_t end; uint8_t base, fail, flags; } q = {-1, 0u, 0, 0, 0};
+            {
                 if (cc3_cid != hint) {                                   // (the kernel follows the tile's first line)
                     const uint32_t L = (uint32_t)(t.name_off[hint + 1] - t.name_off[hint]) + 1u;
                     for (uint32_t k = 0; k < Q3_ROWS_WORDS; k++) rows[k] = t.q3rows[(size_t)hint * SITE_Q3ROWS_WORDS + k];   // (as build_host_sites made them)

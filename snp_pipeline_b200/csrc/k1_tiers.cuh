@@ -3,7 +3,6 @@
 #pragma once
 #include "internal.h"
 #include "line_fast.cuh"
-#include "line_quick.cuh"
 #include "line_general.cuh"
 
 namespace snpgpu {

@@ -22,9 +22,44 @@
 // [limit, limit + QUICK_PAD) of the window.  Any byte values are safe: every word that takes part in a SWAR test is OR-ed
 // into a guard, and a byte >= 0x80 declines the line.
 #pragma once
-#include "line_quick.cuh"
+#include "line_fast.cuh"
 
 namespace snpgpu {
+
+enum : int { ST_DETAIL = 67 };         // "not for this tier": the line goes to the follow-up kernel, no side effects
+constexpr uint32_t QUICK_PAD = 32;     // '\n' sentinels the caller keeps behind `limit` (word over-reads land there)
+
+// acc + 128 * (number of bytes of `flags` that are 0x80); flags holds 0x80 / 0x00 bytes only
+SNP_HD uint32_t flag_sum(uint32_t flags, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(flags, 0x01010101u, acc);
+#else
+    return acc + 128u * (uint32_t)__builtin_popcount(flags);
+#endif
+}
+
+SNP_HD uint32_t funnel_l8(uint32_t lo, uint32_t hi) {       // (hi << 8) | (lo >> 24)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, 8);
+#else
+    return (hi << 8) | (lo >> 24);
+#endif
+}
+
+SNP_HD SiteWord load_site_word(const SiteWord *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return SiteWord{v.x, v.y, v.z, v.w};
+#else
+    return *p;
+#endif
+}
+
+// value of four decimal digit bytes (0..9 each, most significant in the lowest byte)
+SNP_HD uint32_t digits4_value(uint32_t w) {
+    const uint32_t p = (w * 10u + (w >> 8)) & 0x00ff00ffu;    // byte 0: d0 d1, byte 2: d2 d3
+    return (p & 0xffffu) * 100u + (p >> 16);
+}
 
 constexpr uint32_t Q3_NAMEW = 20;      // words per alignment row of the cached contig name (names up to 63 bytes; rows 16-byte aligned)
 constexpr uint32_t Q3_MASK8_W = 4u * Q3_NAMEW;             // word offset of the [4][8] masks of the first eight words
