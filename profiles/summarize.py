@@ -31,12 +31,15 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+KEEP += ["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
 with open(os.path.join(HERE, "%s_k1_metrics.csv" % tag), "w") as f:
     f.write("metric,unit,value\n")
-    f.write("kernel,,%s\n" % m.get("Kernel Name", ("", "?"))[1].replace(",", ";"))
-    for k in hdr:
-        if k in KEEP or k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio"):
-            f.write("%s,%s,%s\n" % (k, m[k][0], m[k][1]))
+    for krow in rows[2:]:                              # every kernel of the capture (the pileup kernel, its follow-up kernel)
+        mk = {h: (u, v) for h, u, v in zip(hdr, units, krow)}
+        f.write("kernel,,%s\n" % mk.get("Kernel Name", ("", "?"))[1].replace(",", ";"))
+        for k in hdr:
+            if k in KEEP or k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio"):
+                f.write("%s,%s,%s\n" % (k, mk[k][0], mk[k][1]))
 
 
 def to_bytes(key):
@@ -48,7 +51,9 @@ def to_bytes(key):
 traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
 json.dump({"dram_bytes_per_launch": traffic, "dram_bytes_read": to_bytes("dram__bytes_read.sum"),
            "dram_bytes_write": to_bytes("dram__bytes_write.sum"), "source": os.path.basename(rep),
-           "workload": "one synthetic 5 Mbp sample, all-positions mode (profiles/run_k1.py)"},
+           "workload": "k1_pileup_kernel over a batch of TWO synthetic 5 Mbp samples, all-positions mode (profiles/run_k1.py, "
+                       "BATCH=2): divide by 2 for the per-sample figure",
+           "dram_bytes_per_sample": traffic / 2},
           open(os.path.join(HERE, "k1_traffic.json"), "w"), indent=1)
 
 for script, out in (("ncu_lines.py", "%s_k1_lines.txt"), ("ncu_regions.py", "%s_k1_regions.txt")):
