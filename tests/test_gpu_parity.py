@@ -555,6 +555,22 @@ def test_merge_sites_random(ctx, n_samples, per_sample, seed):
     assert int(gc.sum()) == keys.size
 
 
+def test_merge_sites_key_bytes(ctx):
+    """K2's radix passes follow the key bytes that carry information: all-zero keys (no pass at all), positions up to
+    2^31 - 1 with chromosome ranks up to 70 000 (seven key bytes), one key repeated by every sample."""
+    rng = np.random.default_rng(12)
+    cases = [
+        (np.zeros(5000, np.uint64), np.arange(5000, dtype=np.uint32) % 7),
+        ((rng.integers(0, 70000, 300000).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 2 ** 31, 300000).astype(np.uint64),
+         np.sort(rng.integers(0, 900, 300000)).astype(np.uint32)),
+        (np.full(4097, (3 << 32) | 77, np.uint64), np.arange(4097, dtype=np.uint32)),
+    ]
+    for keys, samp in cases:
+        wu, wc, ws = orc.merge_sites_keys(keys, samp)
+        gu, gc, gs = ctx.merge_sites(keys, samp)
+        assert np.array_equal(wu, gu) and np.array_equal(wc, gc) and np.array_equal(ws, gs)
+
+
 # ------------------------------------------------------------------------------------------ K4
 @pytest.mark.parametrize("dataset,suffix", [("lambda", ""), ("lambda", "_preserved"), ("agona", ""), ("listeria", ""),
                                             ("listeria", "_preserved")])
