@@ -22,6 +22,7 @@ struct HostWin {                // line_quick3.cuh's memory policy over a plain 
     uint32_t ld(uint32_t k) const { return p[k]; }
     uint32_t tab16(uint32_t k) const { return tab[k]; }
     void ld4(uint32_t k, uint32_t *w) const { w[0] = p[k]; w[1] = p[k + 1]; w[2] = p[k + 2]; w[3] = p[k + 3]; }
+    uint32_t byte(uint32_t off) const { return reinterpret_cast<const uint8_t *>(p)[off]; }
     uint32_t row(uint32_t k) const { return p[k]; }
     void row4(uint32_t k, uint32_t *w) const { ld4(k, w); }
 };
@@ -29,7 +30,7 @@ struct HostWin {                // line_quick3.cuh's memory policy over a plain 
 extern "C" {
 
 // counters[0] = lines, [1] = parsed, [2] = lines through the general path, [3] = error offset, [4] = error code,
-// [5] = lines decided by the first-tier parser
+// [5] = lines decided by the first-tier parser, [6] = of those, lines that needed its token-skipping second look
 int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, const int32_t *name_off,
                   int32_t n_contigs, const int32_t *snp_contig, const int64_t *snp_pos, size_t n_snp,
                   const int32_t *exc_contig, const int64_t *exc_pos, size_t n_exc, const CallParams *p, int all_positions,
@@ -55,7 +56,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
     // classic-Mac line ends: what snpgpu_normalize_newlines_dev does before the kernel is run again (api.cu)
     for (size_t i = 0; i < nbytes; i++)
         if (buf[i] == '\r' && buf[i + 1] != '\n') buf[i] = '\n';
-    uint64_t n_lines = 0, n_parsed = 0, n_general = 0, n_quick = 0;
+    uint64_t n_lines = 0, n_parsed = 0, n_general = 0, n_quick = 0, n_second = 0;
     int hint = 0;
     size_t s = 0;
     counters[3] = ~0ull; counters[4] = 0;
@@ -97,6 +98,11 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
                         SiteWord sw{0u, 0u, 0u, 0u};
                         if (known) sw = t.words[widx];
                         st = q3_rest(m, q3.after, (uint32_t)nbytes, *p, 1u, &q3);
+                        if (st == ST_DETAIL) {                           // the follow-up kernel's second look: indel tokens skipped
+                            st = q3_rest<true>(m, q3.after, (uint32_t)e, *p, 1u, &q3);
+                            if (st == ST_OK && q3.end != e) st = ST_DETAIL;
+                            if (st == ST_OK) n_second++;
+                        }
                         if (st == ST_OK) {
                             uint32_t fl3;
                             q3_site(sw, bb, &q.site, &fl3);
@@ -169,7 +175,7 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
         uint64_t c = cells[h.snp_unique[k]];
         row_out[k] = c ? (uint8_t)(c & 0xff) : (uint8_t)'-';
     }
-    counters[0] = n_lines; counters[1] = n_parsed; counters[2] = n_general; counters[5] = n_quick;
+    counters[0] = n_lines; counters[1] = n_parsed; counters[2] = n_general; counters[5] = n_quick; counters[6] = n_second;
     return (int)counters[4];
 }
 

@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         push = true;
                         push_len = e < wlen || eof ? e - s : 0u;
                         push_flag = odd ? 1u : 0u;
+                        push_cid = keyok ? (uint32_t)(cc.cid + 1) : 0u;
                         next = e + 1u;
                     }
                 } else {
@@ -310,6 +311,7 @@ struct GmemWin {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + k));
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
+    __device__ __forceinline__ uint32_t byte(uint32_t off) const { return __ldg(reinterpret_cast<const uint8_t *>(p) + off); }
     __device__ __forceinline__ uint32_t row(uint32_t k) const { return __ldg(rows + k); }
     __device__ __forceinline__ void row4(uint32_t k, uint32_t *w) const {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rows + k));
@@ -318,10 +320,11 @@ struct GmemWin {
     __device__ __forceinline__ uint32_t tab16(uint32_t k) const { return tab[k]; }
 };
 
-// A queued line whose key columns the pileup kernel took (sites mode: a line at a site) through the first tier again,
-// densely -- 32 such lines per warp.  true: decided (cell stored); false: on to the second tier.
+// A queued line whose key columns the pileup kernel took (default mode: a line at a site; all-positions mode: a line the
+// first look declined) through the first tier again, densely -- 32 such lines per warp -- and with indel tokens skipped.
+// true: decided (cell / per-line result stored); false: on to the second tier.
 __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S, const uint16_t *tab, uint32_t cid,
-                                              unsigned long long goff, uint32_t len, uint32_t one) {
+                                              unsigned long long goff, uint32_t len, uint32_t line_idx, uint32_t one) {
     if (len == 0u || goff + (unsigned long long)len + 48ull > S.nbytes) return false;     // (the words read reach past the line)
     const unsigned long long abase = goff & ~15ull;
     const GmemWin m{reinterpret_cast<const uint32_t *>(S.text + abase), g.sites.q3rows + (size_t)cid * SITE_Q3ROWS_WORDS, tab};
@@ -330,11 +333,12 @@ __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S,
     q3_contig_set(&cc, 0u, (uint32_t)g.sites.len1[cid], (int32_t)cid, g.sites.max_pos[cid], g.sites.bit_base[cid]);
     Q3Line q;
     if (!q3_key(m, s, limit, cc, one, &q)) return false;
-    if ((int32_t)q.pos > cc.max_pos) return false;
-    const uint32_t widx = cc.word_base + (q.pos >> 5), bb = q.pos & 31u;
-    const SiteWord sw = load_site_word(g.sites.words + widx);
-    if (!((sw.any >> bb) & 1u)) return false;
-    if (q3_rest(m, q.after, limit, g.p, one, &q) != ST_OK || q.end != limit) return false;
+    const bool all = g.mode == SNPGPU_MODE_ALL;
+    SiteWord sw{0u, 0u, 0u, 0u};
+    const uint32_t bb = q.pos & 31u;
+    if ((int32_t)q.pos <= cc.max_pos) sw = load_site_word(g.sites.words + cc.word_base + (q.pos >> 5));
+    if (!all && !((sw.any >> bb) & 1u)) return false;
+    if (q3_rest<true>(m, q.after, limit, g.p, one, &q) != ST_OK || q.end != limit) return false;
     unsigned fail = q.fail;
     if ((sw.exc >> bb) & 1u) fail |= FAIL_REGION;
     const unsigned cell = fail ? (unsigned)'-' : q.base;
@@ -345,6 +349,16 @@ __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S,
     if (S.rec_off) {                                          // the VCF pass wants to know which lines were parsed
         const unsigned long long k = atomicAdd(S.rec_count, 1ull);
         if (k < S.rec_cap) S.rec_off[k] = goff;
+    }
+    if (all && S.stage) {                                     // slot [tile][k][lane] of the lane that owns the '\n' in front of the line
+        const unsigned long long tl = (goff ? goff - 1ull : 0ull) / (unsigned long long)K1_LANE_BYTES;
+        const uint16_t v = (uint16_t)(cell | (fail << 8));
+        if (line_idx < (uint32_t)K1_LCAP) {
+            S.stage[((tl >> 5) * (unsigned long long)K1_LCAP + line_idx) * 32ull + (tl & 31ull)] = v;
+        } else {
+            const unsigned long long n = atomicAdd(&S.st->over_used, 1ull);
+            if (n < g.over_cap) S.over[n] = (tl << 32) | ((unsigned long long)(line_idx & 0xffffu) << 16) | (unsigned long long)v;
+        }
     }
     return true;
 }
@@ -365,8 +379,8 @@ __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1
         if (e0 == K1_Q_EMPTY) continue;
         const unsigned long long e1 = g.queue[2ull * i + 1ull];
         const uint32_t cid1 = (uint32_t)(e1 >> 40);
-        const bool quick = !HAS_QUAL && g.mode == SNPGPU_MODE_SITES && cid1 != 0u && !(e1 & K1_Q_GENERAL) &&
-                           k1_rest_quick(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), g.one);
+        const bool quick = !HAS_QUAL && cid1 != 0u && !(e1 & K1_Q_GENERAL) &&
+                           k1_rest_quick(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), k1_entry_idx(e0), g.one);
         {   // one add per warp and sample, not one per line
             const uint32_t act = __activemask();
             const uint32_t same = __match_any_sync(act, quick ? (uint32_t)e1 : 0xffffffffu);

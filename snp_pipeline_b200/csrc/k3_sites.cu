@@ -4,10 +4,9 @@
 // (utils.write_list_of_snps utils.py:1056-1070 -> utils.read_snp_position_list utils.py:1073-1088) and every
 // call_consensus process builds its set of positions from that file (call_consensus.py:133, :147-151).  When both
 // steps run in one process on one GPU the list never has to leave HBM: the sorted unique keys K2 wrote are turned
-// into the table K1 probes (sites.cuh) by two small kernels and one device scan (CUB: library code, as in k2_merge.cu).
+// into the table K1 probes (sites.cuh) by four small kernels: set the bits, prefix sum of the words' popcounts (one block:
+// 156 k words for 5 Mbp), pack the per-word records, resolve every snplist entry to its unique-site index.
 #include "internal.h"
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
 
 namespace snpgpu {
 
@@ -44,15 +43,24 @@ __global__ void k3_unique_kernel(const unsigned long long *keys, size_t n, int n
     snp_unique[i] = u;
 }
 
-struct PopcOp {
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &w) const {
-#if defined(__CUDA_ARCH__)
-        return (uint32_t)__popc(w);
-#else
-        return (uint32_t)__builtin_popcount(w);
-#endif
+// rank[w] = number of set bits in bits[0 .. w): exclusive prefix over the words' popcounts, one block
+constexpr int K3_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(K3_SCAN_THREADS) k3_rank_kernel(const uint32_t *bits, size_t n_words, uint32_t *rank) {
+    __shared__ uint32_t part[K3_SCAN_THREADS];
+    const size_t per = (n_words + K3_SCAN_THREADS - 1) / K3_SCAN_THREADS;
+    const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < n_words ? lo + per : n_words;
+    uint32_t s = 0;
+    for (size_t i = lo; i < hi; i++) s += (uint32_t)__popc(bits[i]);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < K3_SCAN_THREADS; t++) { const uint32_t v = part[t]; part[t] = run; run += v; }
     }
-};
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (size_t i = lo; i < hi; i++) { rank[i] = run; run += (uint32_t)__popc(bits[i]); }
+}
 
 // bits + rank -> the packed words of the first-tier parser (every site is a snplist entry, none is excluded)
 __global__ void k3_pack_words_kernel(const uint32_t *bits, const uint32_t *rank, size_t n_words, SiteWord *words) {
@@ -60,12 +68,7 @@ __global__ void k3_pack_words_kernel(const uint32_t *bits, const uint32_t *rank,
     if (w < n_words) words[w] = SiteWord{bits[w], bits[w], 0u, rank[w]};
 }
 
-size_t k3_scan_bytes(size_t n_words) {
-    size_t b = 0;
-    cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(nullptr, PopcOp());
-    cub::DeviceScan::ExclusiveSum(nullptr, b, in, (uint32_t *)nullptr, (int64_t)n_words);
-    return b;
-}
+size_t k3_scan_bytes(size_t) { return 0; }                   // (the rank kernel needs no workspace)
 
 // bits / rank: n_words words each, bits zeroed here; returns the number of kernels launched, or < 0
 int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
@@ -77,14 +80,14 @@ int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int
         k3_set_bits_kernel<<<(unsigned)((n + 256) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, flags);
         launches++;
     }
-    cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> in(bits, PopcOp());
-    if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, rank, (int64_t)n_words, stream) != cudaSuccess) return -1;
+    (void)tmp; (void)tmp_bytes;
+    k3_rank_kernel<<<1, K3_SCAN_THREADS, 0, stream>>>(bits, n_words, rank);
     k3_pack_words_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(bits, rank, n_words, words);
     if (n) {
         k3_unique_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, rank, snp_unique);
         launches++;
     }
-    return launches + 3;
+    return launches + 2;
 }
 
 // ---- reference bases at the snplist positions (utils.write_reference_snp_file, utils.py:1091-1110): out[k] =

@@ -206,7 +206,10 @@ SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, u
 }
 
 // ---- columns 3-6 of a line whose key columns q3_key() took.  ST_OK (out->end / base / fail filled) or ST_DETAIL. --------
-template <class M>
+// INDEL (the follow-up kernel's dense second look): indel tokens [+-]<n><n letters> (pileup.py:315-320) of up to 999 bases
+// are skipped byte-wise -- the bytes in front of the sign count like any others, the word loop starts again behind the
+// token; anything else about a token (no digits, more than three, a symbol that is no letter / '*' inside it) declines.
+template <bool INDEL = false, class M>
 SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, uint32_t one, Q3Line *out) {
     const uint32_t H = 0x80808080u;
     // ---- columns 3-4: one letter, tab, 1..3 digits (not all '0'), tab -- the 8 bytes at offset i -------------------
@@ -243,6 +246,47 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     uint32_t low;
     for (;;) {
         low = Q3_NADD(0x5f5f5f5fu, w) & H;                 // bit 7 <-> byte < 0x21
+        if (INDEL) {
+            const uint32_t first = low & (0u - low);
+            const uint32_t valid = low ? (first - 1u) & H : H;                                 // the column's bytes of this word
+            const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & valid;
+            const uint32_t part = funnel_l8(prevcar, car);
+            const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);
+            const uint32_t sign = ~(y3 | part) & valid;                                          // ) + - / that is no "^x" quality
+            if (sign) {
+                const uint32_t fs = sign & (0u - sign);
+                const uint32_t sb = (uint32_t)ctz32(fs) >> 3;                                    // byte of the sign in the word
+                const uint32_t ch = (w >> (8u * sb)) & 0xffu;
+                if (ch != '+' && ch != '-') return ST_DETAIL;
+                const uint32_t v2 = (fs - 1u) & H;                                               // the bytes in front of the sign
+                guard |= w & v2;
+                const uint32_t car2 = car & v2, part2 = part & v2;
+                const uint32_t dol2 = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & v2;
+                const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);
+                const uint32_t dck2 = ~(y2 | part) & v2;
+                const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);
+                an1 |= ~(yr | part) & v2;
+                an2 |= car2 & part2;
+                a_rem = flag_sum(car2 | part2 | dol2, a_rem);
+                a_dc = flag_sum(dck2, a_dc);
+                a_dot = flag_sum(dck2 & (w << 6), a_dot);
+                uint32_t t = 4u * k + sb + 1u, n = 0, nd = 0;                                    // the token: 1..3 digits, n symbols
+                while (nd < 3u && (uint32_t)m.byte(t) - '0' < 10u) { n = n * 10u + ((uint32_t)m.byte(t) - '0'); t++; nd++; }
+                if (nd == 0u || (uint32_t)m.byte(t) - '0' < 10u || t + n > limit) return ST_DETAIL;   // a bare sign, a long number
+                for (uint32_t x = 0; x < n; x++) {
+                    const uint32_t c2 = m.byte(t + x);
+                    if ((c2 | 0x20u) - 'a' >= 26u && c2 != '*') return ST_DETAIL;
+                }
+                a_rem += 128u * (1u + nd + n);
+                const uint32_t wpos = t + n;                                                      // go on behind the token
+                k = wpos >> 2;
+                w = m.ld(k);
+                const uint32_t mk = 0xffffffffu << ((wpos & 3u) * 8u);
+                w = (w & mk) | (0x30303030u & ~mk);
+                prevcar = 0;
+                continue;
+            }
+        }
         if (low) break;
         guard |= w;
         const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & H;         // '^'

@@ -47,7 +47,7 @@ def run_sim(L, text, snps, excl, ps, all_pos, force_general=False):
     row = np.zeros(max(len(snps), 1), dtype=np.uint8)
     cap = buf.size + 2
     lines = np.zeros(cap, dtype=np.uint16)
-    counters = np.zeros(6, dtype=np.uint64)
+    counters = np.zeros(8, dtype=np.uint64)
     ptr = lambda a: ctypes.c_void_p(a.ctypes.data) if a.size else None
     rc = L.cpusim_pileup(ptr(buf), buf.size, blob, ptr(off), len(names), ptr(sc), ptr(sp), len(snps), ptr(ec), ptr(ep),
                          len(excl), ctypes.byref(p), 1 if all_pos else 0, 1 if force_general else 0, ptr(row),
@@ -286,7 +286,8 @@ def test_indel_tokens_in_the_first_tier(sim, seed):
     snps = [(linegen.CHROM, p) for p in sorted(rng.sample(range(1, n + 1), 150))]
     for all_pos in (False, True):
         c = _compare(sim, text, snps, [], PARAM_SETS[seed % 4], all_pos)
-        assert c[1] > 0
+        if all_pos and PARAM_SETS[seed % 4][0] <= 0:
+            assert c[6] > 0.5 * n * 0.3, "the token-skipping second look should decide most indel lines (%d)" % c[6]
 
 
 @pytest.mark.parametrize("seed", range(6))
