@@ -222,6 +222,18 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
                               snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec,
                               snpgpu_vcf_alt *alt_out, size_t alt_cap, size_t *n_alt);
 
+/* ---- K7: which SNPs lie in an abnormal region.  Replaces find_dense_regions (filter_regions.py:17-71),
+ *      utils.merge_regions (utils.py:1168-1282) and utils.in_region (utils.py:1285-1318) as filter_regions.py:296-303,
+ *      375-383, 386-428 use them.  snp_keys[i] = group << 48 | contig rank << 32 | position, the SNPs of one sample's contig
+ *      forming a segment sorted by position (filter_regions.py:421), seg_last[i] = index of the last SNP of i's segment;
+ *      group = 0 for every sample in mode "all", the sample's index in mode "each".  For every (max_snps[q], window[q]) pair
+ *      a SNP whose window holds more than max_snps[q] SNPs starts a dense region; edge_keys / edge_end give the contigs' edge
+ *      regions (same key layout, start in the position field).  removed_out[i] = 1 when SNP i lies in a dense or an edge
+ *      region of its (group, contig).  Host buffers; copies inside the call. ------------------------------------ */
+int snpgpu_filter_regions(snpgpu_ctx *ctx, const uint64_t *snp_keys, const uint32_t *seg_last, size_t n, const int32_t *max_snps,
+                          const int32_t *window, int32_t n_params, const uint64_t *edge_keys, const uint32_t *edge_end,
+                          size_t n_edges, uint8_t *removed_out);
+
 /* ---- K6: the pileup by-product of collect_metrics.  Replaces the loop of collect_metrics.py:322-329: the sum over all
  *      lines of int(line.split()[3]) -- the raw-depth column -- where lines without a fourth token or with one that is
  *      no integer add nothing; the caller divides by the reference length and prints "%.2f" (collect_metrics.py:333-338).

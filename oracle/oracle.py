@@ -21,6 +21,7 @@ import itertools
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 
@@ -474,3 +475,103 @@ def distance_texts(seqs):
     for i, a in enumerate(ids):
         mat.append("%s\t%s\n" % (a, "\t".join(str(int(x)) for x in d[i])))
     return "".join(pair), "".join(mat)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# filter_regions: the arithmetic and the file split, restated in plain Python
+# ---------------------------------------------------------------------------------------------------------------
+def merge_regions(regions):
+    """utils.py:1168-1282: coalesce overlapping, contained and adjacent (start, end) regions."""
+    if len(regions) == 0:
+        return regions
+    regions = sorted(regions)
+    merged = [regions[0]]
+    for start, end in regions[1:]:
+        last_start, last_end = merged[-1]
+        if start >= last_start and end <= last_end:
+            continue
+        if start <= last_end + 1 and end > last_end:
+            merged[-1] = (last_start, end)
+        else:
+            merged.append((start, end))
+    return merged
+
+
+def in_region(pos, regions):
+    """utils.py:1285-1318."""
+    return any(start <= pos <= end for start, end in regions)
+
+
+def find_dense_regions(max_allowed_snps, window_size, snps):
+    """filter_regions.py:17-71 over a sorted list of positions."""
+    out = []
+    for idx, pos_start in enumerate(snps):
+        if idx + max_allowed_snps < len(snps):
+            pos_end = snps[idx + max_allowed_snps]
+            if pos_start + window_size - 1 >= pos_end:
+                out.append((pos_start, pos_end))
+    return merge_regions(out)
+
+
+def collect_dense_regions(records, bad_regions, contig_length, edge_length, max_snps_list, window_size_list):
+    """filter_regions.py:386-428: records = [(chrom, pos)] of one sample; bad_regions (chrom -> list) is extended."""
+    snp_dict = {}
+    for chrom, pos in records:
+        snp_dict.setdefault(chrom, []).append(pos)
+    for contig, snp_list in snp_dict.items():
+        if contig not in bad_regions:
+            length = contig_length.get(contig, sys.maxsize)
+            if length <= edge_length * 2:
+                bad_regions[contig] = [(0, length)]
+            else:
+                bad_regions[contig] = [(0, edge_length), (length - edge_length, length)]
+        sorted_snps = sorted(snp_list)
+        for max_allowed, window in zip(max_snps_list, window_size_list):
+            bad_regions[contig].extend(find_dense_regions(max_allowed, window, sorted_snps))
+
+
+def filter_regions_flags(samples, contig_length, edge_length=500, window_size_list=(1000,), max_snps_list=(3,), mode="all",
+                         outgroup=()):
+    """removed[s][r] for record r of sample s (None for an outgroup sample: its file is copied, filter_regions.py:431-457).
+    samples: [(sample_id, [(chrom, pos) in file order])].  filter_regions.py:203-303 (mode "all") / :306-383 ("each")."""
+    flags = []
+    if mode == "all":
+        bad = {}
+        for sid, records in samples:
+            if sid not in outgroup:
+                collect_dense_regions(records, bad, contig_length, edge_length, max_snps_list, window_size_list)
+        bad = {c: merge_regions(r) for c, r in bad.items()}
+        for sid, records in samples:
+            flags.append(None if sid in outgroup else [in_region(p, bad[c]) for c, p in records])
+    else:
+        for sid, records in samples:
+            if sid in outgroup:
+                flags.append(None)
+                continue
+            bad = {}
+            collect_dense_regions(records, bad, contig_length, edge_length, max_snps_list, window_size_list)
+            bad = {c: merge_regions(r) for c, r in bad.items()}
+            flags.append([in_region(p, bad[c]) for c, p in records])
+    return flags
+
+
+def vcf_split_texts(vcf_text, flags):
+    """(preserved, removed) file texts of filter_regions.py:460-520 for a VarScan-style VCF.  PyVCF3's Writer puts the
+    template's header back as: the plain ##key=value lines, then ##INFO, ##FORMAT, ##FILTER, ##ALT, ##contig, then the column
+    line; records are echoed (PyVCF3 round-trips the VarScan records of the reference's data sets character for character:
+    pinned by the lambda / agona golden files).  flags None: the outgroup form (header only in the removed file)."""
+    lines = [ln for ln in vcf_text.split("\n") if ln.strip()]
+    meta = [ln for ln in lines if ln.startswith("##")]
+    rest = [ln for ln in lines if not ln.startswith("##")]
+    kinds = ("##INFO=", "##FORMAT=", "##FILTER=", "##ALT=", "##contig=")
+    head = [ln for ln in meta if not ln.startswith(kinds)]
+    for k in kinds:
+        head += [ln for ln in meta if ln.startswith(k)]
+    head = "".join(ln + "\n" for ln in head + rest[:1])
+    records = rest[1:]
+    if flags is None:
+        return vcf_text, head
+    assert len(flags) == len(records)
+    keep = "".join(ln + "\n" for ln, f in zip(records, flags) if not f)
+    drop = "".join(ln + "\n" for ln, f in zip(records, flags) if f)
+    return head + keep, head + drop

@@ -28,6 +28,7 @@ EXPORTS = [
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_pairwise_distance_tiles_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites", "snpgpu_pileup_depth_sum", "snpgpu_pileup_depth_sum_dev",
+    "snpgpu_filter_regions",
 ]
 
 
@@ -154,6 +155,8 @@ def load():
     L.snpgpu_pairwise_distance_dev.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp]
     L.snpgpu_pairwise_distance_tiles_dev.restype = ctypes.c_int
     L.snpgpu_pairwise_distance_tiles_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp]
+    L.snpgpu_filter_regions.restype = ctypes.c_int
+    L.snpgpu_filter_regions.argtypes = [vp, vp, vp, sz, vp, vp, i32, vp, vp, sz, vp]
     L.snpgpu_pileup_depth_sum.restype = ctypes.c_int
     L.snpgpu_pileup_depth_sum.argtypes = [vp, vp, sz, P(ctypes.c_int64), P(u64), P(u64)]
     L.snpgpu_pileup_depth_sum_dev.restype = ctypes.c_int
@@ -408,6 +411,20 @@ class Context(object):
                 arr[k] = PileupSample(tp or None, int(nb), rp or None, lp or None, int(lc), sp or None)
         self._check(self.lib.snpgpu_pileup_consensus_batch_dev(self.handle, arr, len(arr), sites.handle,
                                                                ctypes.byref(params), mode))
+
+    # -- K7 ---------------------------------------------------------------------------------------
+    def filter_regions(self, snp_keys, seg_last, max_snps, window, edge_keys, edge_end):
+        """removed[i] for SNP i (snpgpu_filter_regions): keys = group << 48 | contig rank << 32 | pos, segments sorted."""
+        k = np.ascontiguousarray(snp_keys, dtype=np.uint64)
+        last = np.ascontiguousarray(seg_last, dtype=np.uint32)
+        mx = np.ascontiguousarray(max_snps, dtype=np.int32)
+        win = np.ascontiguousarray(window, dtype=np.int32)
+        ek = np.ascontiguousarray(edge_keys, dtype=np.uint64)
+        ee = np.ascontiguousarray(edge_end, dtype=np.uint32)
+        out = np.zeros(k.size, dtype=np.uint8)
+        self._check(self.lib.snpgpu_filter_regions(self.handle, _np_ptr(k), _np_ptr(last), k.size, _np_ptr(mx), _np_ptr(win),
+                                                   mx.size, _np_ptr(ek), _np_ptr(ee), ek.size, _np_ptr(out)))
+        return out.astype(bool)
 
     # -- K6 ---------------------------------------------------------------------------------------
     def pileup_depth_sum(self, text):

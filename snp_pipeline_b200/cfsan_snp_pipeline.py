@@ -1,9 +1,9 @@
-"""`cfsan_snp_pipeline`-compatible dispatcher for the four hot-path subcommands.
+"""`cfsan_snp_pipeline`-compatible dispatcher for the hot-path subcommands.
 
-Mirror of snppipeline/cfsan_snp_pipeline.py for merge_sites / call_consensus / snp_matrix / distance: the same flags,
-defaults and validators (cfsan_snp_pipeline.py:329-457), the same `func` / `excepthook` binding (:339-340, :409-410,
-:442-443, :456-457) and the same entry points (parse_argument_list, run_command_from_args, run_command_from_arg_list,
-run_command_from_line, main).  The other eleven subcommands are outside this build.
+Mirror of snppipeline/cfsan_snp_pipeline.py for filter_regions / merge_sites / call_consensus / snp_matrix / distance /
+snp_reference: the same flags, defaults and validators (cfsan_snp_pipeline.py:307-457, :528-543), the same `func` /
+`excepthook` binding (:323-324, :339-340, :409-410, :442-443, :456-457) and the same entry points (parse_argument_list, run_command_from_args, run_command_from_arg_list,
+run_command_from_line, main).  The other subcommands are outside this build.
 
     python -m snp_pipeline_b200.cfsan_snp_pipeline call_consensus -l snplist.txt -o s1/consensus.fasta s1/reads.all.pileup
 """
@@ -13,7 +13,7 @@ import argparse
 import sys
 
 from . import __version__
-from . import call_consensus, distance, merge_sites, snp_matrix, snp_reference, utils
+from . import call_consensus, distance, filter_regions, merge_sites, snp_matrix, snp_reference, utils
 
 
 def _min_cons_freq(value):
@@ -40,6 +40,34 @@ def parse_argument_list(argv):
     subparsers = parser.add_subparsers(dest="subparser_name", help=None, metavar="subcommand")
     subparsers.required = True
     ver = dict(action="version", version="%(prog)s version " + __version__)
+
+    sp = subparsers.add_parser("filter_regions", help="Remove abnormally dense SNPs from all samples", formatter_class=fc,
+                               description="Remove abnormally dense SNPs from the input VCF file, save the reserved SNPs into "
+                                           "a new VCF file, and save the removed SNPs into another VCF file.",
+                               epilog='You can filter snps more than once by specifying multiple window sizes and max snps.  '
+                                      'For example "-m 3 2 -w 1000 100" will filter more than 3 snps in 1000 bases and also '
+                                      'more than 2 snps in 100 bases.')
+    sp.add_argument(dest="sampleDirsFile", type=str, help="File containing a list of directories -- one per sample")
+    sp.add_argument(dest="refFastaFile", type=str, help="Relative or absolute path to the reference fasta file")
+    sp.add_argument("-f", "--force", dest="forceFlag", action="store_true",
+                    help="Force processing even when result files already exist and are newer than inputs")
+    sp.add_argument("-n", "--vcfname", dest="vcfFileName", type=str, default="var.flt.vcf", metavar="NAME",
+                    help="File name of the input VCF files which must exist in each of the sample directories")
+    sp.add_argument("-l", "--edge_length", dest="edgeLength", type=int, default=500, metavar="EDGE_LENGTH",
+                    help="The length of the edge regions in a contig, in which all SNPs will be removed.")
+    sp.add_argument("-w", "--window_size", dest="windowSizeList", type=int, default=[1000], nargs="*", metavar="WINDOW_SIZE",
+                    help="The length of the window in which the number of SNPs should be no more than max_num_snp.")
+    sp.add_argument("-m", "--max_snp", dest="maxSnpsList", type=int, default=[3], nargs="*", metavar="MAX_NUM_SNPs",
+                    help="The maximum number of SNPs allowed in a window.")
+    sp.add_argument("-g", "--out_group", dest="outGroupFile", type=str, default=None, metavar="OUT_GROUP",
+                    help="Relative or absolute path to the file indicating outgroup samples, one sample ID per line.")
+    sp.add_argument("-M", "--mode", dest="mode", choices=["all", "each"], default="all",
+                    help="Control whether dense snp regions found in any sample are filtered from all of the samples, or "
+                         "each sample independently.")
+    sp.add_argument("-v", "--verbose", dest="verbose", type=int, default=1, metavar="0..5",
+                    help="Verbose message level (0=no info, 5=lots)")
+    sp.add_argument("--version", **ver)
+    sp.set_defaults(func=filter_regions.filter_regions, excepthook=utils.handle_global_exception)
 
     sp = subparsers.add_parser("merge_sites", help="Prepare the list of sites having SNPs", formatter_class=fc,
                                description="Combine the SNP positions across all samples into a single unified SNP "
@@ -144,7 +172,20 @@ def parse_argument_list(argv):
     sp.add_argument("--version", **ver)
     sp.set_defaults(func=snp_reference.create_snp_reference_seq, excepthook=utils.handle_global_exception)
 
-    return parser.parse_args(argv)
+    args = parser.parse_args(argv)
+
+    if args.subparser_name == "filter_regions":             # cfsan_snp_pipeline.py:529-543
+        if len(args.windowSizeList) != len(args.maxSnpsList):
+            utils.global_error("Error: you must specify the same number of arguments for window size and max snps.")
+        for window_size in args.windowSizeList:
+            if window_size < 1:
+                utils.global_error("Error: the length of the window must be a positive integer, and the input is %d." % window_size)
+        for max_snps in args.maxSnpsList:
+            if max_snps < 1:
+                utils.global_error("Error: the maximum number of SNPs allowed must be a positive integer, and the input is %d." % max_snps)
+        if args.edgeLength < 1:
+            utils.global_error("Error: the length of the edge regions must be a positive integer, and the input is %d." % args.edgeLength)
+    return args
 
 
 def parse_command_line(line):

@@ -812,6 +812,44 @@ int snpgpu_pileup_want_vcf_records(snpgpu_ctx *ctx, int on) {
     return SNPGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------ K7
+int snpgpu_filter_regions(snpgpu_ctx *ctx, const uint64_t *snp_keys, const uint32_t *seg_last, size_t n, const int32_t *max_snps,
+                          const int32_t *window, int32_t n_params, const uint64_t *edge_keys, const uint32_t *edge_end,
+                          size_t n_edges, uint8_t *removed_out) {
+    if (!ctx || n_params < 0 || (n && (!snp_keys || !seg_last || !removed_out)) || (n_params && (!max_snps || !window)) ||
+        (n_edges && (!edge_keys || !edge_end)))
+        return fail(ctx, SNPGPU_E_ARG, "filter_regions: null argument");
+    if (n == 0) return SNPGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_last = up(n * 8), o_max = o_last + up(n * 4), o_win = o_max + up((size_t)n_params * 4 + 4);
+    const size_t o_ek = o_win + up((size_t)n_params * 4 + 4), o_ee = o_ek + up(n_edges * 8 + 8), o_out = o_ee + up(n_edges * 4 + 4);
+    const size_t o_tmp = o_out + up(n);
+    const size_t tb = k7_workspace_bytes(n, n_params, n_edges);
+    CK(ctx->k2_tmp.ensure(o_tmp + tb));
+    uint8_t *b = (uint8_t *)ctx->k2_tmp.p;
+    CK(cudaMemcpyAsync(b, snp_keys, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_last, seg_last, n * 4, cudaMemcpyHostToDevice, st));
+    if (n_params) {
+        CK(cudaMemcpyAsync(b + o_max, max_snps, (size_t)n_params * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b + o_win, window, (size_t)n_params * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (n_edges) {
+        CK(cudaMemcpyAsync(b + o_ek, edge_keys, n_edges * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b + o_ee, edge_end, n_edges * 4, cudaMemcpyHostToDevice, st));
+    }
+    int launches = 0;
+    int rc = k7_launch(st, (const uint64_t *)b, (const uint32_t *)(b + o_last), n, (const int32_t *)(b + o_max),
+                       (const int32_t *)(b + o_win), n_params, (const uint64_t *)(b + o_ek), (const uint32_t *)(b + o_ee), n_edges,
+                       b + o_out, b + o_tmp, tb, &launches);
+    if (rc) return fail(ctx, rc, "filter_regions: launch failed");
+    ctx->launches += (uint64_t)launches;
+    CK(cudaMemcpyAsync(removed_out, b + o_out, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SNPGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------ K6
 int snpgpu_pileup_depth_sum_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nbytes, int64_t *sum_out, uint64_t *lines_out,
                                 uint64_t *error_offset) {

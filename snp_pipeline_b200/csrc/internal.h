@@ -39,6 +39,15 @@ int    k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *samp
                  uint32_t *count_out, uint32_t *samples_out, unsigned long long *n_uniq_dev, void *tmp,
                  size_t tmp_bytes, int *launches);
 
+int    k2_sort_pairs(cudaStream_t stream, const uint64_t *keys, const uint32_t *vals, size_t n, uint32_t *vals_out, void *tmp,
+                     size_t tmp_bytes, const unsigned long long **sorted_keys, void **spare, uint32_t **hist_out, int *launches);
+
+// k7_regions.cu
+int    k7_launch(cudaStream_t stream, const uint64_t *snp_keys, const uint32_t *seg_last, size_t n, const int32_t *max_snps,
+                 const int32_t *window, int n_params, const uint64_t *extra_keys, const uint32_t *extra_end, size_t n_extra,
+                 uint8_t *removed_out, void *tmp, size_t tmp_bytes, int *launches);
+size_t k7_workspace_bytes(size_t n, int n_params, size_t n_extra);
+
 // k4_distance.cu
 size_t k4_workspace_bytes(size_t n_rows, size_t n_sites);
 int    k4_launch(cudaStream_t stream, const uint8_t *matrix, size_t n_rows, size_t n_sites, size_t row_stride,

@@ -173,13 +173,10 @@ __global__ void k2_counts_kernel(const uint32_t *start, const unsigned long long
     if (k < nu) count_out[k] = (k + 1 < nu ? start[k + 1] : (uint32_t)n) - start[k];
 }
 
-int k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *sample_of, size_t n, uint64_t *uniq_out,
-              uint32_t *count_out, uint32_t *samples_out, unsigned long long *n_uniq_dev, void *tmp, size_t tmp_bytes,
-              int *launches) {
-    if (n == 0) {
-        cudaError_t e = cudaMemsetAsync(n_uniq_dev, 0, sizeof(unsigned long long), stream);
-        return e == cudaSuccess ? 0 : SNPGPU_E_CUDA;
-    }
+// Stable sort of (key, value) pairs by key.  tmp: k2_workspace_bytes(n).  *sorted_keys points into tmp (or at `keys` when no
+// key byte carries information); the values land in vals_out; *spare: a key-sized buffer of tmp the result does not use.
+int k2_sort_pairs(cudaStream_t stream, const uint64_t *keys, const uint32_t *vals, size_t n, uint32_t *vals_out, void *tmp,
+                  size_t tmp_bytes, const unsigned long long **sorted_keys, void **spare, uint32_t **hist_out, int *launches) {
     if (n >= ((size_t)1 << 32)) return SNPGPU_E_ARG;
     if (tmp_bytes < k2_workspace_bytes(n)) return SNPGPU_E_NOMEM;
     const size_t nb = k2_blocks(n);
@@ -200,22 +197,40 @@ int k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *sample_
     for (int b = 0; b < 8; b++)
         if ((h_or >> (8 * b)) & 0xffull) shifts[n_pass++] = 8 * b;
     *launches += 1;
-    // ---- the passes: (keys, samples) ping-pong so that the last pass writes the samples into samples_out
+    // ---- the passes: (keys, values) ping-pong so that the last pass writes the values into vals_out
     const unsigned long long *kin = (const unsigned long long *)keys;
-    const uint32_t *vin = sample_of;
+    const uint32_t *vin = vals;
     for (int p = 0; p < n_pass; p++) {
         unsigned long long *kout = kbuf[p & 1];
-        uint32_t *vout = ((n_pass - 1 - p) & 1) ? vtmp : samples_out;
+        uint32_t *vout = ((n_pass - 1 - p) & 1) ? vtmp : vals_out;
         k2_hist_kernel<<<(unsigned)nb, K2_THREADS, 0, stream>>>(kin, n, shifts[p], hist, nb);
         k2_scan_kernel<<<1, K2_SCAN_THREADS, 0, stream>>>(hist, 256 * nb, nullptr);
         k2_scatter_kernel<<<(unsigned)nb, K2_THREADS, 0, stream>>>(kin, vin, n, shifts[p], hist, nb, kout, vout);
         kin = kout; vin = vout;
         *launches += 3;
     }
-    if (n_pass == 0 && cudaMemcpyAsync(samples_out, sample_of, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    if (n_pass == 0 && cudaMemcpyAsync(vals_out, vals, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
         return SNPGPU_E_CUDA;
+    *sorted_keys = kin;
+    *spare = kin == kbuf[0] ? kbuf[1] : kbuf[0];
+    *hist_out = hist;
+    return cudaGetLastError() == cudaSuccess ? 0 : SNPGPU_E_CUDA;
+}
+
+int k2_launch(cudaStream_t stream, const uint64_t *keys, const uint32_t *sample_of, size_t n, uint64_t *uniq_out,
+              uint32_t *count_out, uint32_t *samples_out, unsigned long long *n_uniq_dev, void *tmp, size_t tmp_bytes,
+              int *launches) {
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(n_uniq_dev, 0, sizeof(unsigned long long), stream);
+        return e == cudaSuccess ? 0 : SNPGPU_E_CUDA;
+    }
+    const unsigned long long *kin = nullptr;
+    void *spare = nullptr;
+    uint32_t *hist = nullptr;
+    if (int rc = k2_sort_pairs(stream, keys, sample_of, n, samples_out, tmp, tmp_bytes, &kin, &spare, &hist, launches)) return rc;
+    const size_t nb = k2_blocks(n);
     // ---- unique keys, run starts, run lengths (the key buffer the last pass did not write holds the starts)
-    uint32_t *start = reinterpret_cast<uint32_t *>(kin == kbuf[0] ? kbuf[1] : kbuf[0]);
+    uint32_t *start = reinterpret_cast<uint32_t *>(spare);
     k2_heads_kernel<<<(unsigned)nb, K2_THREADS, 0, stream>>>(kin, n, hist);
     k2_scan_kernel<<<1, K2_SCAN_THREADS, 0, stream>>>(hist, nb, n_uniq_dev);
     k2_unique_kernel<<<(unsigned)nb, K2_THREADS, 0, stream>>>(kin, n, hist, (unsigned long long *)uniq_out, start);

@@ -233,6 +233,28 @@ def convert_vcf_file_to_snp_set(vcf_file_path):
     return set(read_vcf_positions(vcf_file_path))
 
 
+def sample_id_from_file(file_path):
+    """utils.py:459-485: the sample id is the name of the file's directory."""
+    return os.path.basename(os.path.dirname(os.path.abspath(file_path)))
+
+
+def fasta_contig_lengths(fasta_path):
+    """{record id: len(record.seq)} as the SeqIO.parse loop of filter_regions.py:183-192 builds it (a repeated id keeps the
+    last length, lines in front of the first '>' are skipped)."""
+    lengths, cur = {}, None
+    with open(fasta_path, "r") as f:
+        for line in f:
+            if line.startswith(">"):
+                words = line[1:].split(None, 1)
+                if not words:
+                    raise IndexError("list index out of range")
+                cur = words[0]
+                lengths[cur] = 0
+            elif cur is not None:
+                lengths[cur] += len("".join(line.split()))
+    return lengths
+
+
 def fasta_record_text(seq_id, seq):
     """Bio.SeqIO's FastaWriter as call_consensus.py:189-192 drives it (description ""): 60-column lines."""
     parts = [">%s\n" % seq_id]

@@ -11,6 +11,9 @@ Produces
                          files, multi-contig, duplicate positions, CRLF) -> consensus.fasta text or exit code
   references.tar.xz      the three datasets' reference genomes (snp_reference's input)
   doctest_strip.json     the strip doctests of pileup.py:294-309 evaluated by the reference itself
+  ref_regions.json.xz    filter_regions known answers: seeded samples of (contig, position) records pushed through the
+                         reference's collect_dense_regions + utils.merge_regions + utils.in_region in the order
+                         filter_regions_across_samples / filter_regions_per_sample call them -> removed flag per record
 
 Usage:  python tests/golden/make_golden.py      (needs /root/reference; writes next to this script)
 """
@@ -231,11 +234,88 @@ def make_doctest_strip():
     print("wrote doctest_strip.json", len(out))
 
 
+def make_ref_regions():
+    fr = rh.ref("filter_regions")
+    utils = rh.ref("utils")
+
+    class Rec(object):
+        def __init__(self, chrom, pos):
+            self.CHROM, self.POS = chrom, pos
+
+    def flags_of(samples, contig_len, edge, windows, maxs, mode, outgroup):
+        out = []
+        if mode == "all":                                   # filter_regions.py:256-303
+            bad = dict()
+            for sid, recs in samples:
+                if sid not in outgroup:
+                    fr.collect_dense_regions([Rec(c, p) for c, p in recs], bad, contig_len, edge, maxs, windows)
+            for contig, regions in bad.items():
+                bad[contig] = utils.merge_regions(regions)
+            for sid, recs in samples:
+                out.append(None if sid in outgroup else [bool(utils.in_region(p, bad[c])) for c, p in recs])
+        else:                                               # filter_regions.py:352-383
+            for sid, recs in samples:
+                if sid in outgroup:
+                    out.append(None)
+                    continue
+                bad = dict()
+                fr.collect_dense_regions([Rec(c, p) for c, p in recs], bad, contig_len, edge, maxs, windows)
+                for contig, regions in bad.items():
+                    bad[contig] = utils.merge_regions(regions)
+                out.append([bool(utils.in_region(p, bad[c])) for c, p in recs])
+        return out
+
+    rng = random.Random(77)
+    cases = []
+    for k in range(120):
+        n_contigs = rng.choice([1, 1, 2, 5])
+        contigs = ["ctg%d" % i for i in range(n_contigs)]
+        contig_len = {c: rng.choice([300, 900, 5000, 60000, 4000000]) for c in contigs}
+        if k % 7 == 3:
+            del contig_len[contigs[-1]]                     # a contig the reference fasta does not hold (sys.maxsize)
+        edge = rng.choice([1, 50, 500, 500, 2000])
+        n_par = rng.choice([1, 1, 2, 3])
+        windows = [rng.choice([1, 2, 10, 100, 1000, 1000, 5000]) for _ in range(n_par)]
+        maxs = [rng.choice([1, 2, 3, 3, 5, 10]) for _ in range(n_par)]
+        samples = []
+        for s in range(rng.choice([1, 2, 4, 6])):
+            recs = []
+            for c in contigs:
+                top = min(contig_len.get(c, 100000), 200000)
+                n = rng.choice([0, 1, 3, 10, 40, 150])
+                if rng.random() < 0.5:                      # clustered
+                    centres = [rng.randint(1, top) for _ in range(max(1, n // 8))]
+                    pos = [max(1, min(top, int(rng.gauss(rng.choice(centres), rng.choice([3, 60, 400]))))) for _ in range(n)]
+                else:
+                    pos = [rng.randint(1, top) for _ in range(n)]
+                if rng.random() < 0.7:
+                    pos = sorted(pos)
+                if rng.random() < 0.5:
+                    pos = list(dict.fromkeys(pos))
+                recs += [(c, p) for p in pos]
+            samples.append(("sample%d" % s, recs))
+        outgroup = ["sample1"] if k % 5 == 4 else []
+        for mode in ("all", "each"):
+            cases.append({"samples": samples, "contig_len": contig_len, "edge": edge, "windows": windows, "maxs": maxs,
+                          "mode": mode, "outgroup": outgroup,
+                          "removed": flags_of(samples, contig_len, edge, windows, maxs, mode, outgroup)})
+    doc = []                                                # the doctests of filter_regions.py:38-58 / utils.py:1185-1262
+    for maxs_, win, snps in ((3, 1000, []), (3, 1000, [1, 2, 3]), (3, 1000, [1, 2, 3, 1000]), (3, 1000, [1, 2, 3, 999, 1000]),
+                             (3, 1000, [1, 2, 3, 1000, 1001, 1002, 1500]), (3, 1000, [1, 2, 3, 1000, 3001, 3002, 3003, 4000]),
+                             (1, 1, [5, 5, 6]), (2, 10, [1, 5, 10, 11, 30, 31, 39])):
+        doc.append({"max": maxs_, "window": win, "snps": snps, "regions": fr.find_dense_regions(maxs_, win, snps)})
+    dump_xz("ref_regions.json.xz", {"cases": cases, "dense": doc})
+
+
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference tree not mounted at %s" % rh.REFERENCE_ROOT)
+    if sys.argv[1:] == ["regions"]:
+        make_ref_regions()
+        sys.exit(0)
     make_datasets()
     make_references()
     make_doctest_strip()
     make_ref_lines()
     make_ref_files()
+    make_ref_regions()
