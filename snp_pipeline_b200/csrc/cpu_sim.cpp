@@ -98,9 +98,13 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
                         SiteWord sw{0u, 0u, 0u, 0u};
                         if (known) sw = t.words[widx];
                         st = q3_rest(m, q3.after, (uint32_t)nbytes, *p, 1u, &q3);
-                        if (st == ST_DETAIL) {                           // the follow-up kernel's second look: indel tokens skipped
+                        if (st == ST_TALLY) {                            // well-formed, only the call is left: queued with its end known
+                            if (q3.end != e) { counters[3] = s; counters[4] = 94; break; }   // harness self-check: that end
+                            st = ST_DETAIL;
+                        } else if (st == ST_DETAIL) {                    // the follow-up kernel's second look: indel tokens skipped
                             st = q3_rest<true>(m, q3.after, (uint32_t)e, *p, 1u, &q3);
                             if (st == ST_OK && q3.end != e) st = ST_DETAIL;
+                            if (st == ST_TALLY) st = ST_DETAIL;
                             if (st == ST_OK) n_second++;
                         }
                         if (st == ST_OK) {

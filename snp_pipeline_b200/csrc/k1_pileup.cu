@@ -52,6 +52,7 @@ struct SmemWin {                                // line_quick3.cuh's memory poli
 
 // queue entry, second word: sample | flags << 32 | (contig of the line + 1, when its key columns were taken) << 40
 enum : unsigned long long { K1_Q_GENERAL = 1ull << 32 };     // odd bytes seen: straight to line_general.cuh
+enum : unsigned long long { K1_Q_TALLY = 1ull << 33 };       // the first tier took the whole line, the call needs tallies: second tier
 constexpr unsigned long long K1_Q_EMPTY = ~0ull;             // first word of a slot its warp claimed and did not fill
 constexpr int K1_QBLOCK = 64;                                // queue entries a warp claims at a time
 
@@ -224,6 +225,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         }
                         n_ok++;
                         next = q.end + 1u;
+                    } else if (st == ST_TALLY && q.end < wlen) {      // well-formed, the reference base does not win: its end is known
+                        push = true;
+                        push_len = q.end - s;
+                        push_flag = 2u;
+                        push_cid = (uint32_t)(cc.cid + 1);
+                        next = q.end + 1u;
                     } else {
                         uint32_t odd = 0;
                         const uint32_t e = q3_find_nl(m, s, one, &odd);
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                 const unsigned long long slot = q_base + q_used + (unsigned long long)__popc(pb & ((1u << lane) - 1u));
                 if (push && slot < g.queue_cap) {
                     g.queue[2ull * slot] = k1_entry(cnt, push_len, base + s);
-                    g.queue[2ull * slot + 1ull] = (unsigned long long)si | (push_flag ? K1_Q_GENERAL : 0ull) | ((unsigned long long)push_cid << 40);
+                    g.queue[2ull * slot + 1ull] = (unsigned long long)si | ((unsigned long long)push_flag << 32) | ((unsigned long long)push_cid << 40);
                 }
                 q_used += np;
             }
@@ -320,14 +327,57 @@ struct GmemWin {
     __device__ __forceinline__ uint32_t tab16(uint32_t k) const { return tab[k]; }
 };
 
+// The follow-up kernel's copy of a line: every thread brings its line into its own K1_RSTAGE bytes of shared memory with
+// independent 16-byte loads (one exposed latency instead of one per word the parsers look at), from the 16-byte boundary in
+// front of the line to 48 bytes behind it (what the first tier's word loads may touch).  Lines that do not fit, lines of
+// unknown length and the last lines of a text are parsed where they lie.
+constexpr uint32_t K1_RSTAGE = 208;
+struct StagedWin {
+    const uint32_t *p;
+    const uint32_t *rows;
+    const uint16_t *tab;
+    __device__ __forceinline__ uint32_t ld(uint32_t k) const { return p[k]; }
+    __device__ __forceinline__ void ld4(uint32_t k, uint32_t *w) const {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p + k);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    __device__ __forceinline__ uint32_t byte(uint32_t off) const { return reinterpret_cast<const uint8_t *>(p)[off]; }
+    __device__ __forceinline__ uint32_t row(uint32_t k) const { return __ldg(rows + k); }
+    __device__ __forceinline__ void row4(uint32_t k, uint32_t *w) const {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rows + k));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    __device__ __forceinline__ uint32_t tab16(uint32_t k) const { return tab[k]; }
+};
+__device__ __forceinline__ bool k1_rest_stage(const K1Samp &S, unsigned long long goff, uint32_t len, uint8_t *mine) {
+    const unsigned long long abase = goff & ~15ull;
+    const uint32_t need = (uint32_t)(goff - abase) + len + 48u;
+    const uint32_t chunks = (need + 15u) >> 4;
+    if (len == 0u || need > K1_RSTAGE || abase + 16ull * chunks > S.nbytes) return false;
+    const uint4 *src = reinterpret_cast<const uint4 *>(S.text + abase);
+    uint4 *dst = reinterpret_cast<uint4 *>(mine);
+    constexpr uint32_t NC = K1_RSTAGE / 16u, HALF = (NC + 1u) / 2u;
+    uint4 v[HALF];                                            // (two rounds: half the registers of one)
+#pragma unroll
+    for (uint32_t r = 0; r < 2u; r++) {
+#pragma unroll
+        for (uint32_t c = 0; c < HALF; c++) if (r * HALF + c < chunks) v[c] = __ldg(src + r * HALF + c);
+#pragma unroll
+        for (uint32_t c = 0; c < HALF; c++) if (r * HALF + c < chunks) dst[r * HALF + c] = v[c];
+    }
+    return true;
+}
+
 // A queued line whose key columns the pileup kernel took (default mode: a line at a site; all-positions mode: a line the
 // first look declined) through the first tier again, densely -- 32 such lines per warp -- and with indel tokens skipped.
 // true: decided (cell / per-line result stored); false: on to the second tier.
+template <class WIN>
 __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S, const uint16_t *tab, uint32_t cid,
-                                              unsigned long long goff, uint32_t len, uint32_t line_idx, uint32_t one) {
+                                              unsigned long long goff, uint32_t len, uint32_t line_idx, uint32_t one,
+                                              const uint8_t *staged) {
     if (len == 0u || goff + (unsigned long long)len + 48ull > S.nbytes) return false;     // (the words read reach past the line)
     const unsigned long long abase = goff & ~15ull;
-    const GmemWin m{reinterpret_cast<const uint32_t *>(S.text + abase), g.sites.q3rows + (size_t)cid * SITE_Q3ROWS_WORDS, tab};
+    const WIN m{reinterpret_cast<const uint32_t *>(staged ? staged : S.text + abase), g.sites.q3rows + (size_t)cid * SITE_Q3ROWS_WORDS, tab};
     const uint32_t s = (uint32_t)(goff - abase), limit = s + len;      // (the line's own '\n' stands where the sentinels would)
     Q3Contig cc;
     q3_contig_set(&cc, 0u, (uint32_t)g.sites.len1[cid], (int32_t)cid, g.sites.max_pos[cid], g.sites.bit_base[cid]);
@@ -366,6 +416,8 @@ __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S,
 template <bool HAS_QUAL>
 __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1Batch g) {
     __shared__ uint16_t tab[2 * Q3_TABN];
+    __shared__ __align__(16) uint8_t stage_s[128 * K1_RSTAGE];
+    uint8_t *mine = stage_s + threadIdx.x * K1_RSTAGE;
     for (uint32_t k = threadIdx.x; k < 2u * Q3_TABN; k += blockDim.x) tab[k] = (uint16_t)q3_tab_entry(k, g.p);
     __syncthreads();
     unsigned long long n = *g.queue_count;
@@ -379,8 +431,12 @@ __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1
         if (e0 == K1_Q_EMPTY) continue;
         const unsigned long long e1 = g.queue[2ull * i + 1ull];
         const uint32_t cid1 = (uint32_t)(e1 >> 40);
-        const bool quick = !HAS_QUAL && cid1 != 0u && !(e1 & K1_Q_GENERAL) &&
-                           k1_rest_quick(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), k1_entry_idx(e0), g.one);
+        const bool staged = !(e1 & K1_Q_GENERAL) && k1_rest_stage(g.s[(uint32_t)e1], k1_entry_goff(e0), k1_entry_len(e0), mine);
+        bool quick = false;
+        if (!HAS_QUAL && cid1 != 0u && !(e1 & (K1_Q_GENERAL | K1_Q_TALLY))) {
+            if (staged) quick = k1_rest_quick<StagedWin>(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), k1_entry_idx(e0), g.one, mine);
+            else quick = k1_rest_quick<GmemWin>(g, g.s[(uint32_t)e1], tab, cid1 - 1u, k1_entry_goff(e0), k1_entry_len(e0), k1_entry_idx(e0), g.one, nullptr);
+        }
         {   // one add per warp and sample, not one per line
             const uint32_t act = __activemask();
             const uint32_t same = __match_any_sync(act, quick ? (uint32_t)e1 : 0xffffffffu);
@@ -392,8 +448,9 @@ __global__ void __launch_bounds__(128) k1_rest_kernel(const __grid_constant__ K1
         cs.n_parsed = cs.n_general = 0u;
         bool more = true;
         if (!(e1 & K1_Q_GENERAL)) {
-            if (g.mode == SNPGPU_MODE_ALL) more = k1_detail<HAS_QUAL, true>(a, cs, k1_entry_goff(e0), k1_entry_idx(e0), k1_entry_len(e0));
-            else more = k1_detail<HAS_QUAL, false>(a, cs, k1_entry_goff(e0), k1_entry_idx(e0), k1_entry_len(e0));
+            const uint8_t *st_buf = staged ? mine : nullptr;
+            if (g.mode == SNPGPU_MODE_ALL) more = k1_detail<HAS_QUAL, true>(a, cs, k1_entry_goff(e0), k1_entry_idx(e0), k1_entry_len(e0), st_buf);
+            else more = k1_detail<HAS_QUAL, false>(a, cs, k1_entry_goff(e0), k1_entry_idx(e0), k1_entry_len(e0), st_buf);
         }
         if (more) k1_general(a, cs, k1_entry_goff(e0), k1_entry_idx(e0));
         if (cs.n_parsed) atomicAdd(&a.st->n_parsed, (unsigned long long)cs.n_parsed);
@@ -547,6 +604,10 @@ int k1_blocks_per_sm() {
     int n0 = 0, n1 = 0;
     cudaFuncSetAttribute(k1_pileup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
     cudaFuncSetAttribute(k1_pileup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
+    // the follow-up kernel runs between two pileup kernels: it keeps their shared-memory carve-out (a different split of
+    // L1 / shared memory between consecutive kernels costs a reconfiguration each time, and measured as noise)
+    cudaFuncSetAttribute(k1_rest_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k1_rest_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, k1_pileup_kernel<false>, K1_THREADS, k1_smem_bytes());
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k1_pileup_kernel<true>, K1_THREADS, k1_smem_bytes());
     return n0 < n1 ? n0 : n1;

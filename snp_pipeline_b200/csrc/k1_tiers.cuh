@@ -118,15 +118,15 @@ __device__ __forceinline__ uint32_t k1_find_nl(const uint8_t *buf, uint32_t s, u
     return cap;
 }
 
-// second tier: exact tallies (line_fast.cuh) on the text in global memory; returns true when the line has to
+// second tier: exact tallies (line_fast.cuh) on the text in global memory (or the thread's staged copy); returns true when the line has to
 // go on to k1_general().  The words line_fast reads may reach 7 bytes past the line end, so the last lines of
 // the text are left to k1_general(), which reads byte by byte.
 template <bool HAS_QUAL, bool ALL>
 __device__ __noinline__ bool k1_detail(const PileupArgs &a, K1Cold &cs, unsigned long long goff, uint32_t line_idx,
-                                       uint32_t len_hint) {
+                                       uint32_t len_hint, const uint8_t *staged) {
     const unsigned long long room = a.nbytes - goff;
     const unsigned long long abase = goff & ~15ull;
-    const uint8_t *buf = a.text + abase;
+    const uint8_t *buf = staged ? staged : a.text + abase;    // (staged: the thread's copy of [abase, line end + 48) in shared memory)
     const uint32_t s = (uint32_t)(goff - abase);
     const uint32_t cap = room < 65536ull ? (uint32_t)room : 65536u;
     const uint32_t n = len_hint && len_hint < cap ? len_hint : k1_find_nl(buf, s, cap);

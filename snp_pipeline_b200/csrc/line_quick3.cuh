@@ -27,6 +27,8 @@
 namespace snpgpu {
 
 enum : int { ST_DETAIL = 67 };         // "not for this tier": the line goes to the follow-up kernel, no side effects
+enum : int { ST_TALLY = 68 };          // declined like ST_DETAIL, but the line is well-formed and out->end is its '\n':
+                                       // only the call needs the per-letter tallies of the second tier
 constexpr uint32_t QUICK_PAD = 32;     // '\n' sentinels the caller keeps behind `limit` (word over-reads land there)
 
 // acc + 128 * (number of bytes of `flags` that are 0x80); flags holds 0x80 / 0x00 bytes only
@@ -38,6 +40,15 @@ SNP_HD uint32_t flag_sum(uint32_t flags, uint32_t acc) {
 #endif
 }
 
+// acc + 128 * (sum of the bytes of w whose byte in `flags` is 0x80); flags holds 0x80 / 0x00 bytes only
+SNP_HD uint32_t flag_weigh(uint32_t w, uint32_t flags, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(w, flags, acc);
+#else
+    for (int b = 0; b < 4; b++) acc += ((w >> (8 * b)) & 0xffu) * ((flags >> (8 * b)) & 0xffu);
+    return acc;
+#endif
+}
 SNP_HD uint32_t funnel_l8(uint32_t lo, uint32_t hi) {       // (hi << 8) | (lo >> 24)
 #if defined(__CUDA_ARCH__)
     return __funnelshift_l(lo, hi, 8);
@@ -205,7 +216,7 @@ SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, u
     return !bad;
 }
 
-// ---- columns 3-6 of a line whose key columns q3_key() took.  ST_OK (out->end / base / fail filled) or ST_DETAIL. --------
+// ---- columns 3-6 of a line whose key columns q3_key() took.  ST_OK (out->end / base / fail filled), ST_TALLY (out->end) or ST_DETAIL. --------
 // INDEL (the follow-up kernel's dense second look): indel tokens [+-]<n><n letters> (pileup.py:315-320) of up to 999 bases
 // are skipped byte-wise -- the bytes in front of the sign count like any others, the word loop starts again behind the
 // token; anything else about a token (no digits, more than three, a symbol that is no letter / '*' inside it) declines.
@@ -241,7 +252,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         const uint32_t mk = 0xffffffffu << ((b0 & 3u) * 8u);
         w = (w & mk) | (0x30303030u & ~mk);
     }
-    uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', kept '.')
+    uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', sum of the kept '.'/',' bytes)
     uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0, guard = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
     uint32_t low;
     for (;;) {
@@ -269,7 +280,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
                 an2 |= car2 & part2;
                 a_rem = flag_sum(car2 | part2 | dol2, a_rem);
                 a_dc = flag_sum(dck2, a_dc);
-                a_dot = flag_sum(dck2 & (w << 6), a_dot);
+                a_dot = flag_weigh(w, dck2, a_dot);
                 uint32_t t = 4u * k + sb + 1u, n = 0, nd = 0;                                    // the token: 1..3 digits, n symbols
                 while (nd < 3u && (uint32_t)m.byte(t) - '0' < 10u) { n = n * 10u + ((uint32_t)m.byte(t) - '0'); t++; nd++; }
                 if (nd == 0u || (uint32_t)m.byte(t) - '0' < 10u || t + n > limit) return ST_DETAIL;   // a bare sign, a long number
@@ -301,7 +312,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         an2 |= car & part;                                 // "^^"
         a_rem = flag_sum(car | part | dol, a_rem);
         a_dc = flag_sum(dck, a_dc);
-        a_dot = flag_sum(dck & (w << 6), a_dot);           // bit 1 -> bit 7: '.' not ','
+        a_dot = flag_weigh(w, dck, a_dot);                 // 128 x (0x2c per kept ',' + 0x2e per kept '.')
         prevcar = car;
         w = m.ld(++k);
     }
@@ -323,7 +334,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         an2 |= (car & part) | (part & first);                              // "^" + separator: trailing '^'
         a_rem = flag_sum((car | part | dol) & valid, a_rem);
         a_dc = flag_sum(dck, a_dc);
-        a_dot = flag_sum(dck & (w << 6), a_dot);
+        a_dot = flag_weigh(w, dck, a_dot);
         if (((w >> (8u * j)) & 0xffu) != '\t') an2 |= H;                   // the column ends in a tab
         q0 = 4u * k + j + 1u;
     }
@@ -357,9 +368,9 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         if ((acc & H) != H || (good & below) != (below & H) || ((v >> (8u * r)) & 0xffu) != '\n') return ST_DETAIL;
     }
     // ---- call (pileup.py:550-588): the reference base wins outright ---------------------------------
-    const uint32_t dc = a_dc >> 7, dot = a_dot >> 7;
-    if (dc <= nb - dc) return ST_DETAIL;
+    const uint32_t dc = a_dc >> 7, dot = ((a_dot >> 7) - 0x2cu * dc) >> 1;     // (0x2c nc + 0x2e nd - 0x2c (nc + nd)) / 2
     out->end = qe;
+    if (dc <= nb - dc) return ST_TALLY;
     out->base = (uint8_t)ref;
     out->fail = q3_filter(m, nb, dc, dot, dc - dot, p);
     return ST_OK;
