@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
         } else {
             static_assert(K1_LANE_BYTES % 16 == 0, "the search reads whole 16-byte chunks of the lane's range");
             uint32_t p = r1;
+            uint4 vn = *reinterpret_cast<const uint4 *>(buf + r0);
             for (uint32_t c0 = r0; c0 < r1; c0 += 16u) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(buf + c0);
+                const uint4 v = vn;
+                vn = *reinterpret_cast<const uint4 *>(buf + c0 + 16u);          // (the next chunk, a trip ahead; the last one reads into the next lane's range or the look-ahead)
                 const uint32_t x0 = v.x ^ 0x0a0a0a0au, x1 = v.y ^ 0x0a0a0a0au, x2 = v.z ^ 0x0a0a0a0au, x3 = v.w ^ 0x0a0a0a0au;
                 const uint32_t z0 = (x0 - 0x01010101u) & ~x0 & 0x80808080u, z1 = (x1 - 0x01010101u) & ~x1 & 0x80808080u;
                 const uint32_t z2 = (x2 - 0x01010101u) & ~x2 & 0x80808080u, z3 = (x3 - 0x01010101u) & ~x3 & 0x80808080u;

@@ -195,10 +195,10 @@ template <class M>
 SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, uint32_t one, Q3Line *out) {
     const uint32_t H = 0x80808080u;
     out->after = s; out->pos = 0u;
-    if (!q3_name(m, s, limit, cc)) return false;
-    // 1..8 digits + tab behind the name, as the 8 bytes at offset i (nine digits or more: next tier)
+    if (cc.len1 == 0u || s + cc.len1 + 24u > limit + QUICK_PAD) return false;      // (q3_name's own range check, first)
     const uint32_t i = s + cc.len1, k = i >> 2, sh = i << 3;
-    const uint32_t a = m.ld(k), b = m.ld(k + 1u), c = m.ld(k + 2u);
+    const uint32_t a = m.ld(k), b = m.ld(k + 1u), c = m.ld(k + 2u);                  // asked for together with the name's words
+    if (!q3_name(m, s, limit, cc)) return false;
     const uint32_t rl = funnel_r(a, b, sh), rh = funnel_r(b, c, sh);
     const uint32_t xl = rl ^ 0x30303030u, xh = rh ^ 0x30303030u;                      // digits -> 0..9
     const uint32_t ndl = Q3_ADD(0x76767676u, xl) & H, ndh = Q3_ADD(0x76767676u, xh) & H;   // bit 7: not a digit
@@ -216,6 +216,28 @@ SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, u
     return !bad;
 }
 
+#ifndef Q3_LOOPN
+#define Q3_LOOPN 4            // words of the bases column per trip of the first tier's loop
+#endif
+// one whole word of the bases column (no separator in it): classes, anomalies, counts
+#define Q3_BASES_WORD(w) do { \
+        guard |= w; \
+        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & H; \
+        const uint32_t part = funnel_l8(prevcar, car); \
+        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & H; \
+        const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu); \
+        const uint32_t dck = ~(y2 | part) & H; \
+        const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u); \
+        const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb); \
+        an0 |= ~(y3 | part); \
+        an1 |= ~(yr | part); \
+        an2 |= car & part; \
+        a_rem = flag_sum(car | part | dol, a_rem); \
+        a_dc = flag_sum(dck, a_dc); \
+        a_dot = flag_weigh(w, dck, a_dot); \
+        prevcar = car; \
+    } while (0)
+
 // ---- columns 3-6 of a line whose key columns q3_key() took.  ST_OK (out->end / base / fail filled), ST_TALLY (out->end) or ST_DETAIL. --------
 // INDEL (the follow-up kernel's dense second look): indel tokens [+-]<n><n letters> (pileup.py:315-320) of up to 999 bases
 // are skipped byte-wise -- the bytes in front of the sign count like any others, the word loop starts again behind the
@@ -225,11 +247,12 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     const uint32_t H = 0x80808080u;
     // ---- columns 3-4: one letter, tab, 1..3 digits (not all '0'), tab -- the 8 bytes at offset i -------------------
     uint32_t x0, x1;
+    const uint32_t hw1 = m.ld((i >> 2) + 1u), hw2 = m.ld((i >> 2) + 2u);   // (one of them holds the first bases too)
     {
-        const uint32_t k = i >> 2, sh = i << 3;
-        const uint32_t a = m.ld(k), b = m.ld(k + 1u), c = m.ld(k + 2u);
-        x0 = funnel_r(a, b, sh);
-        x1 = funnel_r(b, c, sh);
+        const uint32_t sh = i << 3;
+        const uint32_t a = m.ld(i >> 2);
+        x0 = funnel_r(a, hw1, sh);
+        x1 = funnel_r(hw1, hw2, sh);
     }
     const unsigned ref = x0 & 0xffu;
     bool bad = ((ref | 0x20u) - 'a') >= 26u;              // a letter: '.'/',' stand for REF / ref (pileup.py:255-256)
@@ -247,7 +270,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     const uint32_t refb = (ref | 0x20u) * 0x01010101u;
     const uint32_t MFD = one * 0xfdfdfdfdu, MF9 = one * 0xf9f9f9f9u;   // (in registers: one LOP3 per masked compare)
     uint32_t k = b0 >> 2;
-    uint32_t w = m.ld(k);
+    uint32_t w = k == (i >> 2) + 1u ? hw1 : hw2;           // b0 = i + 4 .. i + 6: no load, no wait
     {   // the bytes of the first word in front of the column become a symbol that counts nowhere
         const uint32_t mk = 0xffffffffu << ((b0 & 3u) * 8u);
         w = (w & mk) | (0x30303030u & ~mk);
@@ -255,6 +278,15 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', sum of the kept '.'/',' bytes)
     uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0, guard = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
     uint32_t low;
+#if Q3_LOOPN > 1
+    uint32_t wn = INDEL ? 0u : m.ld(k + 1u);
+#endif
+#if Q3_LOOPN > 2
+    uint32_t wn2 = INDEL ? 0u : m.ld(k + 2u);
+#endif
+#if Q3_LOOPN > 3
+    uint32_t wn3 = INDEL ? 0u : m.ld(k + 3u);
+#endif
     for (;;) {
         low = Q3_NADD(0x5f5f5f5fu, w) & H;                 // bit 7 <-> byte < 0x21
         if (INDEL) {
@@ -299,24 +331,34 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
             }
         }
         if (low) break;
-        guard |= w;
-        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & H;         // '^'
-        const uint32_t part = funnel_l8(prevcar, car);                                       // the byte after a '^'
-        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & H;         // '$'
-        const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);           // bit 7 clear <-> ',' or '.'
-        const uint32_t dck = ~(y2 | part) & H;                                               // kept '.' / ','
-        const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);           // bit 7 clear <-> ) + - /
-        const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);                  // bit 7 clear <-> the reference letter
-        an0 |= ~(y3 | part);                               // an indel sign (or ')' '/': next tier) that is no "^x" quality
-        an1 |= ~(yr | part);                               // the reference letter written out
-        an2 |= car & part;                                 // "^^"
-        a_rem = flag_sum(car | part | dol, a_rem);
-        a_dc = flag_sum(dck, a_dc);
-        a_dot = flag_weigh(w, dck, a_dot);                 // 128 x (0x2c per kept ',' + 0x2e per kept '.')
-        prevcar = car;
+#if Q3_LOOPN > 1
+        if (!INDEL) {                                      // several words a trip, each left as soon as it holds the separator:
+            Q3_BASES_WORD(w);                              // the later words' loads have whole words' work to arrive
+#define Q3_NEXT_WORD(x) w = (x); ++k; low = Q3_NADD(0x5f5f5f5fu, w) & H; if (low) break; Q3_BASES_WORD(w)
+            Q3_NEXT_WORD(wn);
+#if Q3_LOOPN > 2
+            Q3_NEXT_WORD(wn2);
+#endif
+#if Q3_LOOPN > 3
+            Q3_NEXT_WORD(wn3);
+#endif
+#undef Q3_NEXT_WORD
+            w = m.ld(++k);
+            wn = m.ld(k + 1u);
+#if Q3_LOOPN > 2
+            wn2 = m.ld(k + 2u);
+#endif
+#if Q3_LOOPN > 3
+            wn3 = m.ld(k + 3u);
+#endif
+            continue;
+        }
+#endif
+        Q3_BASES_WORD(w);
         w = m.ld(++k);
     }
     uint32_t q0;
+    const uint32_t qw1 = m.ld(k + 1u), qw2 = m.ld(k + 2u); // the quality column starts in this word or the next: asked for now
     {   // the word that holds the separator: the same, restricted to the bytes in front of it
         const uint32_t first = low & (0u - low);
         const uint32_t valid = (first - 1u) & H;
@@ -347,20 +389,22 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     {
         uint32_t kq = q0 >> 2;
         const uint32_t ke = qe >> 2;
-        uint32_t v = m.ld(kq);
+        uint32_t v = kq == k ? w : qw1;
         const uint32_t mk = 0xffffffffu << ((q0 & 3u) * 8u);
         v = (v & mk) | (0x30303030u & ~mk);
         uint32_t acc = H;                                  // bit 7 stays set while every byte is in 0x21..0x7f
-        while (kq + 1u < ke) {                             // two words per step
-            const uint32_t v1 = m.ld(kq + 1u);
+        uint32_t v1 = kq == k ? qw1 : qw2;
+        while (kq + 1u < ke) {                             // two words per step, the next two asked for a step ahead
+            const uint32_t n0 = m.ld(kq + 2u), n1 = m.ld(kq + 3u);
             acc &= Q3_ADD(0x5f5f5f5fu, v) & ~v;
             acc &= Q3_ADD(0x5f5f5f5fu, v1) & ~v1;
             kq += 2u;
-            v = m.ld(kq);
+            v = n0; v1 = n1;
         }
         if (kq < ke) {
             acc &= Q3_ADD(0x5f5f5f5fu, v) & ~v;
-            v = m.ld(++kq);
+            v = v1;
+            ++kq;
         }
         const uint32_t r = qe & 3u;
         const uint32_t below = (0x80u << (8u * r)) - 1u;   // the bytes in front of the terminator (bit 7 of each)
@@ -369,10 +413,11 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     }
     // ---- call (pileup.py:550-588): the reference base wins outright ---------------------------------
     const uint32_t dc = a_dc >> 7, dot = ((a_dot >> 7) - 0x2cu * dc) >> 1;     // (0x2c nc + 0x2e nd - 0x2c (nc + nd)) / 2
+    const uint8_t fail = q3_filter(m, nb, dc, dot, dc - dot, p);
     out->end = qe;
     if (dc <= nb - dc) return ST_TALLY;
     out->base = (uint8_t)ref;
-    out->fail = q3_filter(m, nb, dc, dot, dc - dot, p);
+    out->fail = fail;
     return ST_OK;
 }
 
