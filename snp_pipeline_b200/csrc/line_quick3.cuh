@@ -212,7 +212,9 @@ SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, u
     bool bad = ((rl | rh) & H) != 0u;                     // (a byte >= 0x80 would have fooled the digit test)
     bad |= n == 0u || sep != '\t';
     out->after = i + n + 1u;
-    out->pos = digits4_value(v_lo) * 10000u + digits4_value(v_hi);
+    // d0 .. d7 -> value, as dot products (the FMA pipe's): 100 d0 + 10 d1 + d2 and d3 of each half
+    out->pos = (flag_weigh(v_lo, 0x00010a64u, 0u) * 10u + flag_weigh(v_lo, 0x01000000u, 0u)) * 10000u
+             + flag_weigh(v_hi, 0x00010a64u, 0u) * 10u + flag_weigh(v_hi, 0x01000000u, 0u);
     return !bad;
 }
 
@@ -278,15 +280,10 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', sum of the kept '.'/',' bytes)
     uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0, guard = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
     uint32_t low;
-#if Q3_LOOPN > 1
-    uint32_t wn = INDEL ? 0u : m.ld(k + 1u);
-#endif
-#if Q3_LOOPN > 2
-    uint32_t wn2 = INDEL ? 0u : m.ld(k + 2u);
-#endif
-#if Q3_LOOPN > 3
-    uint32_t wn3 = INDEL ? 0u : m.ld(k + 3u);
-#endif
+    uint32_t wn = 0, wn2 = 0, wn3 = 0;                     // the words behind w, asked for a trip ahead (first look only)
+    if constexpr (Q3_LOOPN > 1 && !INDEL) wn = m.ld(k + 1u);
+    if constexpr (Q3_LOOPN > 2 && !INDEL) wn2 = m.ld(k + 2u);
+    if constexpr (Q3_LOOPN > 3 && !INDEL) wn3 = m.ld(k + 3u);
     for (;;) {
         low = Q3_NADD(0x5f5f5f5fu, w) & H;                 // bit 7 <-> byte < 0x21
         if (INDEL) {
@@ -331,31 +328,21 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
             }
         }
         if (low) break;
-#if Q3_LOOPN > 1
-        if (!INDEL) {                                      // several words a trip, each left as soon as it holds the separator:
+        if constexpr (Q3_LOOPN > 1 && !INDEL) {            // several words a trip, each left as soon as it holds the separator:
             Q3_BASES_WORD(w);                              // the later words' loads have whole words' work to arrive
 #define Q3_NEXT_WORD(x) w = (x); ++k; low = Q3_NADD(0x5f5f5f5fu, w) & H; if (low) break; Q3_BASES_WORD(w)
             Q3_NEXT_WORD(wn);
-#if Q3_LOOPN > 2
-            Q3_NEXT_WORD(wn2);
-#endif
-#if Q3_LOOPN > 3
-            Q3_NEXT_WORD(wn3);
-#endif
+            if constexpr (Q3_LOOPN > 2) { Q3_NEXT_WORD(wn2); }
+            if constexpr (Q3_LOOPN > 3) { Q3_NEXT_WORD(wn3); }
 #undef Q3_NEXT_WORD
             w = m.ld(++k);
             wn = m.ld(k + 1u);
-#if Q3_LOOPN > 2
-            wn2 = m.ld(k + 2u);
-#endif
-#if Q3_LOOPN > 3
-            wn3 = m.ld(k + 3u);
-#endif
-            continue;
+            if constexpr (Q3_LOOPN > 2) wn2 = m.ld(k + 2u);
+            if constexpr (Q3_LOOPN > 3) wn3 = m.ld(k + 3u);
+        } else {
+            Q3_BASES_WORD(w);
+            w = m.ld(++k);
         }
-#endif
-        Q3_BASES_WORD(w);
-        w = m.ld(++k);
     }
     uint32_t q0;
     const uint32_t qw1 = m.ld(k + 1u), qw2 = m.ld(k + 2u); // the quality column starts in this word or the next: asked for now
