@@ -32,9 +32,15 @@ stats = torch.zeros((B, 6), dtype=torch.int64, device="cuda")
 p = _lib.make_params(min_cons_depth=3)
 ctx.enable_timing(True)
 batch = [(buf.data_ptr(), n, row[i].data_ptr(), lines[i].data_ptr(), G + 64, stats[i].data_ptr()) for i in range(B)]
+ctx.pileup_consensus_batch_dev(batch, sites, p, mode)           # (warm-up: buffers grow on the first call)
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record(stream)
 for _ in range(n_launch):
     ctx.pileup_consensus_batch_dev(batch, sites, p, mode)
+ev1.record(stream)
 torch.cuda.synchronize()
 ms, k = ctx.kernel_time(0)
 per = ms / (k * B)
-print("text bytes %d, K1 avg %.4f ms per sample over %d launches of %d samples -> %.1f GB/s; stats %s" % (n, per, k, B, n / per / 1e6, stats[0].tolist()))
+whole = ev0.elapsed_time(ev1) / (n_launch * B)                  # pileup + follow-up + ordering + finish kernels, per sample
+print("text bytes %d, K1 avg %.4f ms per sample over %d launches of %d samples -> %.1f GB/s; whole call %.4f ms per sample; stats %s"
+      % (n, per, k, B, n / per / 1e6, whole, stats[0].tolist()))
