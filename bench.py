@@ -814,6 +814,32 @@ def main():
         e2e = {"value": positions / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "h2d_gbs": h2d / e2e_s / 1e9}
+        # ---- the per-sample call the reference's run.py:709 makes: default mode + consensus.vcf (K1 sites mode, then K5:
+        #      sort of the parsed lines' offsets, tallies, the data lines' text on the device), host buffers, N = 1 only
+        if world == 1:
+            from snp_pipeline_b200 import pileup as gpu_pileup
+            caller = gpu_pileup.ConsensusCaller(0.6, 3, 0, 0.0)
+            ftexts = [";".join(caller.fail_names(mm) or ["PASS"]) for mm in range(_lib.VCF_FILTER_MASKS)]
+            sites_v = _lib.Sites.from_keys_dev(ctx, [CONTIG], [args.genome_len], w.uniq_dev.data_ptr(), n_sites)
+            ctx.want_vcf_records(True)
+            t_call = t_vcf = 0.0
+            n_lines = n_bytes = 0
+            reps = min(3, len(pool))
+            for k in range(reps + 1):                             # (first pass: warm-up)
+                t0 = time.perf_counter()
+                ctx.pileup_consensus(pool[k % len(pool)][:pool_n[k % len(pool)]], sites_v, w.params, w.lib.MODE_SITES)
+                t1 = time.perf_counter()
+                vtext, vrec = ctx.pileup_vcf_text(sites_v, w.params, w.lib.MODE_SITES, ftexts)
+                t2 = time.perf_counter()
+                if k:
+                    t_call += t1 - t0; t_vcf += t2 - t1; n_lines += vrec; n_bytes += len(vtext)
+            ctx.want_vcf_records(False)
+            sites_v.close()
+            e2e["production_call"] = {
+                "what": "call_consensus of one sample as run.py:709 runs it (snplist = the batch's union, --vcfFileName): "
+                        "consensus row + the consensus.vcf data lines, host buffers, wall clock",
+                "pileup_consensus_ms": t_call / reps * 1e3, "vcf_text_ms": t_vcf / reps * 1e3,
+                "vcf_records_per_sample": n_lines // reps, "vcf_bytes_per_sample": n_bytes // reps}
         for o in owners + [rows_owner, lines_owner]:
             o.free()
 

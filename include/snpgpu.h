@@ -222,6 +222,19 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
                               snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec,
                               snpgpu_vcf_alt *alt_out, size_t alt_cap, size_t *n_alt);
 
+/* The same records as the text of the VCF's data lines, in file order, formatted on the device: what
+ * vcf_writer.py:295-379 (_make_vcf_record_from_pileup) + PyVCF3's Writer.write_record print per pileup record:
+ *   CHROM POS . REF ALT . FILTER NS=1 GT:SDP:RD:AD:RDF:RDR:ADF:ADR:FT gt:sdp:rd:ad:rdf:rdr:adf:adr:ft
+ * filter_text: SNPGPU_VCF_FILTER_MASKS NUL-terminated strings of SNPGPU_VCF_FILTER_TEXT bytes each -- the FILTER column of
+ * every SNPGPU_FAIL_* mask ("PASS" for 0, else the caller's filter names joined with ';', pileup.py:550-588 /
+ * call_consensus.py:165-168); failed_snp_gt: '.', '0' or '1' (--vcfFailedSnpGt); preserve_ref_case: --vcfPreserveRefCase.
+ * *n_text = bytes of text (SNPGPU_E_NOMEM when text_cap is smaller: call again with that much room). */
+#define SNPGPU_VCF_FILTER_MASKS 64
+#define SNPGPU_VCF_FILTER_TEXT  64
+int snpgpu_pileup_vcf_text(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                           const char *filter_text, int failed_snp_gt, int preserve_ref_case, char *text_out, size_t text_cap,
+                           size_t *n_text, size_t *n_rec);
+
 /* ---- K7: which SNPs lie in an abnormal region.  Replaces find_dense_regions (filter_regions.py:17-71),
  *      utils.merge_regions (utils.py:1168-1282) and utils.in_region (utils.py:1285-1318) as filter_regions.py:296-303,
  *      375-383, 386-428 use them.  snp_keys[i] = group << 48 | contig rank << 32 | position, the SNPs of one sample's contig

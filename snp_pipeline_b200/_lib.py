@@ -28,7 +28,7 @@ EXPORTS = [
     "snpgpu_merge_sites", "snpgpu_merge_sites_dev", "snpgpu_pairwise_distance", "snpgpu_pairwise_distance_dev",
     "snpgpu_pairwise_distance_tiles_dev",
     "snpgpu_synth_pileup_dev", "snpgpu_synth_sample_sites", "snpgpu_pileup_depth_sum", "snpgpu_pileup_depth_sum_dev",
-    "snpgpu_filter_regions",
+    "snpgpu_filter_regions", "snpgpu_pileup_vcf_text",
 ]
 
 
@@ -52,6 +52,7 @@ class PileupSample(ctypes.Structure):
 
 
 VCF_HAS_DEPTH, VCF_FIRST_IS_REF = 1, 2
+VCF_FILTER_MASKS, VCF_FILTER_TEXT = 64, 64
 
 # snpgpu_vcf_record / snpgpu_vcf_alt (include/snpgpu.h) as numpy record layouts
 VCF_RECORD_DTYPE = np.dtype([("offset", "<u8"), ("pos", "<i8"), ("raw_depth", "<i8"), ("alt_index", "<u8"),
@@ -155,6 +156,8 @@ def load():
     L.snpgpu_pairwise_distance_dev.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp]
     L.snpgpu_pairwise_distance_tiles_dev.restype = ctypes.c_int
     L.snpgpu_pairwise_distance_tiles_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp]
+    L.snpgpu_pileup_vcf_text.restype = ctypes.c_int
+    L.snpgpu_pileup_vcf_text.argtypes = [vp, vp, vp, i32, ctypes.c_char_p, i32, i32, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     L.snpgpu_filter_regions.restype = ctypes.c_int
     L.snpgpu_filter_regions.argtypes = [vp, vp, vp, sz, vp, vp, i32, vp, vp, sz, vp]
     L.snpgpu_pileup_depth_sum.restype = ctypes.c_int
@@ -374,6 +377,31 @@ class Context(object):
             self._check(rc)
             return rec[:n_rec.value], alt[:n_alt.value]
         raise SnpGpuError(E_NOMEM, "pileup_vcf_records: capacities kept growing")
+
+    def pileup_vcf_text(self, sites, params, mode, filter_texts, failed_snp_gt=".", preserve_ref_case=False):
+        """K5 with the formatting on the device: the data lines of the consensus VCF of the preceding pileup_consensus()
+        call as bytes, and their number.  filter_texts: the FILTER column's text for every fail mask 0 .. 63."""
+        assert len(filter_texts) == VCF_FILTER_MASKS
+        table = bytearray(VCF_FILTER_MASKS * VCF_FILTER_TEXT)
+        for m, t in enumerate(filter_texts):
+            b = t.encode("ascii")
+            if len(b) >= VCF_FILTER_TEXT:
+                raise SnpGpuError(E_ARG, "pileup_vcf_text: filter text longer than %d bytes" % (VCF_FILTER_TEXT - 1))
+            table[m * VCF_FILTER_TEXT:m * VCF_FILTER_TEXT + len(b)] = b
+        cap = 1 << 20
+        gt = ord(failed_snp_gt) if failed_snp_gt in (".", "0") else ord("1")
+        for _ in range(3):
+            out = np.empty(cap, dtype=np.uint8)
+            n_text, n_rec = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            rc = self.lib.snpgpu_pileup_vcf_text(self.handle, sites.handle, ctypes.byref(params), mode, bytes(table), gt,
+                                                 1 if preserve_ref_case else 0, _np_ptr(out), cap, ctypes.byref(n_text),
+                                                 ctypes.byref(n_rec))
+            if rc == E_NOMEM and n_text.value > cap:
+                cap = n_text.value
+                continue
+            self._check(rc)
+            return out[:n_text.value].tobytes(), n_rec.value
+        raise SnpGpuError(E_NOMEM, "pileup_vcf_text: capacity kept growing")
 
     def pileup_consensus_begin(self, text, sites, params, mode, row_out, line_out=None, stats=None):
         """First half of the pipelined host-buffer call (snpgpu_pileup_consensus_begin): text / row_out / line_out are

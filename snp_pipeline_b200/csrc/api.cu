@@ -47,7 +47,7 @@ struct snpgpu_ctx {
     bool   rec_valid = false;                 // the last snpgpu_pileup_consensus() left its line list in rec_off ...
     size_t rec_listed = 0;                    // ... this many entries
     int    rec_mode = 0;
-    DevBuf rec_off, rec_sorted, rec_out, alt_out, k5_tmp, k5_state;
+    DevBuf rec_off, rec_sorted, rec_out, alt_out, k5_tmp, k5_state, vcf_text;
     size_t rec_cap = 0;                       // entries of rec_off
     DevBuf k2_tmp, k2_keys, k2_samp, k2_uniq, k2_cnt, k2_out, k2_n;
     DevBuf k4_tmp, k4_mat, k4_dist;
@@ -152,7 +152,7 @@ void snpgpu_destroy(snpgpu_ctx *ctx) {
     }
     if (ctx->lane_event) cudaEventDestroy(ctx->lane_event);
     DevBuf *all[] = {&ctx->k1_zero, &ctx->tile_first, &ctx->tile_lines, &ctx->lane_lines, &ctx->stage, &ctx->over, &ctx->arena, &ctx->queue,
-                     &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out,
+                     &ctx->stats, &ctx->text, &ctx->row, &ctx->lines, &ctx->rec_off, &ctx->rec_sorted, &ctx->rec_out, &ctx->alt_out, &ctx->vcf_text,
                      &ctx->k5_tmp, &ctx->k5_state, &ctx->k2_tmp, &ctx->k2_keys, &ctx->k2_samp,
                      &ctx->k2_uniq, &ctx->k2_cnt, &ctx->k2_out, &ctx->k2_n, &ctx->k4_tmp, &ctx->k4_mat, &ctx->k4_dist,
                      &ctx->synth_tmp, &ctx->synth_n, &ctx->k3_tmp};
@@ -723,12 +723,10 @@ int snpgpu_pileup_consensus_end(snpgpu_ctx *ctx, int slot) {
 }
 
 // ------------------------------------------------------------------------------------------ K5
-int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
-                              snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec, snpgpu_vcf_alt *alt_out,
-                              size_t alt_cap, size_t *n_alt) {
-    if (!ctx || !sites || !params || !n_rec || !n_alt) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null argument");
+// the records and their ALT entries of the staged text, in file order, in ctx->rec_out / ctx->alt_out (device)
+static int k5_records_dev(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode, size_t alt_hint,
+                          size_t *n_rec, size_t *n_alt) {
     if (!ctx->text_valid) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: no staged text (call snpgpu_pileup_consensus first)");
-    if ((rec_cap && !rec_out) || (alt_cap && !alt_out)) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null output");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t nbytes = ctx->text_nbytes;
@@ -761,16 +759,26 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
     *n_rec = n;
     *n_alt = 0;
     if (n == 0) return SNPGPU_OK;
-    // ---- file order
-    const size_t sort_b = k5_sort_bytes(n);
+    // ---- file order: K2's radix sort over the offsets (the values it carries along are not looked at)
+    const size_t sort_b = k2_workspace_bytes(n) + 2 * ((n * sizeof(uint32_t) + 255) & ~(size_t)255);
     CK(ctx->k5_tmp.ensure(sort_b + 256));
     CK(ctx->rec_sorted.ensure(n * sizeof(unsigned long long)));
-    if (k5_sort_offsets(st, (const unsigned long long *)ctx->rec_off.p, (unsigned long long *)ctx->rec_sorted.p, n,
-                        ctx->k5_tmp.p, ctx->k5_tmp.cap))
-        return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: sort failed");      // (CUB's kernels: not counted among the library's own launches)
+    {
+        uint32_t *vin = (uint32_t *)ctx->k5_tmp.p, *vout = vin + ((n + 63) & ~(size_t)63);
+        void *tmp = (uint8_t *)ctx->k5_tmp.p + 2 * ((n * sizeof(uint32_t) + 255) & ~(size_t)255);
+        const unsigned long long *sorted = nullptr;
+        void *spare = nullptr;
+        uint32_t *hist = nullptr;
+        int launches = 0;
+        CK(cudaMemsetAsync(vin, 0, n * sizeof(uint32_t), st));
+        if (k2_sort_pairs(st, (const uint64_t *)ctx->rec_off.p, vin, n, vout, tmp, k2_workspace_bytes(n), &sorted, &spare, &hist, &launches))
+            return fail(ctx, SNPGPU_E_CUDA, "pileup_vcf_records: sort failed");
+        ctx->launches += (uint64_t)launches;
+        CK(cudaMemcpyAsync(ctx->rec_sorted.p, sorted, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    }
     // ---- tallies; ALT entries are claimed with a counter, so the device buffer may have to grow once as well
     CK(ctx->rec_out.ensure(n * sizeof(snpgpu_vcf_record)));
-    size_t alt_room = std::max<size_t>(alt_cap, 2 * n + 64);
+    size_t alt_room = std::max<size_t>(alt_hint, 2 * n + 64);
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(ctx->alt_out.ensure(alt_room * sizeof(snpgpu_vcf_alt)));
         CK(ctx->arena.ensure(ctx->arena_want));
@@ -796,14 +804,65 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
         }
         if (claimed > alt_room) { alt_room = (size_t)claimed; continue; }
         *n_alt = (size_t)claimed;
-        if (n > rec_cap || claimed > alt_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: output capacity too small");
-        CK(cudaMemcpyAsync(rec_out, ctx->rec_out.p, n * sizeof(snpgpu_vcf_record), cudaMemcpyDeviceToHost, st));
-        if (claimed) CK(cudaMemcpyAsync(alt_out, ctx->alt_out.p, (size_t)claimed * sizeof(snpgpu_vcf_alt), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         return SNPGPU_OK;
     }
     return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: scratch kept growing");
 }
+
+int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                              snpgpu_vcf_record *rec_out, size_t rec_cap, size_t *n_rec, snpgpu_vcf_alt *alt_out,
+                              size_t alt_cap, size_t *n_alt) {
+    if (!ctx || !sites || !params || !n_rec || !n_alt) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null argument");
+    if ((rec_cap && !rec_out) || (alt_cap && !alt_out)) return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_records: null output");
+    if (int rc = k5_records_dev(ctx, sites, params, mode, alt_cap, n_rec, n_alt)) return rc;
+    if (*n_rec == 0) return SNPGPU_OK;
+    if (*n_rec > rec_cap || *n_alt > alt_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_records: output capacity too small");
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(rec_out, ctx->rec_out.p, *n_rec * sizeof(snpgpu_vcf_record), cudaMemcpyDeviceToHost, st));
+    if (*n_alt) CK(cudaMemcpyAsync(alt_out, ctx->alt_out.p, *n_alt * sizeof(snpgpu_vcf_alt), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SNPGPU_OK;
+}
+
+// The data lines as text (vcf_writer.py:295-379 + PyVCF3's Writer.write_record), formatted on the device.
+int snpgpu_pileup_vcf_text(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,
+                           const char *filter_text, int failed_snp_gt, int preserve_ref_case, char *text_out, size_t text_cap,
+                           size_t *n_text, size_t *n_rec) {
+    if (!ctx || !sites || !params || !filter_text || !n_text || !n_rec || (text_cap && !text_out))
+        return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_text: null argument");
+    size_t n_alt = 0;
+    *n_text = 0;
+    if (int rc = k5_records_dev(ctx, sites, params, mode, 0, n_rec, &n_alt)) return rc;
+    const size_t n = *n_rec;
+    if (n == 0) return SNPGPU_OK;
+    cudaStream_t st = ctx->stream;
+    const size_t nb = k5_text_blocks(n);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_len = up(SNPGPU_VCF_FILTER_MASKS * SNPGPU_VCF_FILTER_TEXT), o_bsum = o_len + up(n * sizeof(uint32_t));
+    const size_t o_total = o_bsum + up(nb * sizeof(unsigned long long));
+    CK(ctx->k5_tmp.ensure(o_total + 256));
+    uint8_t *b = (uint8_t *)ctx->k5_tmp.p;
+    CK(cudaMemcpyAsync(b, filter_text, SNPGPU_VCF_FILTER_MASKS * SNPGPU_VCF_FILTER_TEXT, cudaMemcpyHostToDevice, st));
+    K5TextArgs a;
+    a.text = (const uint8_t *)ctx->text.p; a.rec = (const snpgpu_vcf_record *)ctx->rec_out.p; a.alt = (const snpgpu_vcf_alt *)ctx->alt_out.p;
+    a.n_rec = n; a.filter_text = (const char *)b; a.failed_snp_gt = (char)failed_snp_gt; a.preserve_ref_case = preserve_ref_case != 0;
+    a.len = (uint32_t *)(b + o_len); a.block_sum = (unsigned long long *)(b + o_bsum); a.total = (unsigned long long *)(b + o_total);
+    a.out = nullptr;
+    ctx->launches += (uint64_t)k5_launch_text_sizes(st, a);
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, a.total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_text = (size_t)total;
+    if (total > text_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_text: output capacity too small");
+    CK(ctx->vcf_text.ensure((size_t)total + 16));
+    a.out = (char *)ctx->vcf_text.p;
+    ctx->launches += (uint64_t)k5_launch_text_write(st, a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(text_out, ctx->vcf_text.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SNPGPU_OK;
+}
+
 
 int snpgpu_pileup_want_vcf_records(snpgpu_ctx *ctx, int on) {
     if (!ctx) return SNPGPU_E_ARG;

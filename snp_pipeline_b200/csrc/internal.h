@@ -13,9 +13,21 @@ int    k1_launch_finish(cudaStream_t stream, const K1Batch &g, int max_tiles, bo
 int    k1_launch_normalize(cudaStream_t stream, uint8_t *text, size_t nbytes);
 
 // k5_vcf.cu
-size_t k5_sort_bytes(size_t n);
-int    k5_sort_offsets(cudaStream_t stream, const unsigned long long *in, unsigned long long *out, size_t n, void *tmp,
-                       size_t tmp_bytes);
+struct K5TextArgs {
+    const uint8_t *text;                  // the staged pileup text (the chromosome column is copied from it)
+    const snpgpu_vcf_record *rec;
+    const snpgpu_vcf_alt *alt;
+    size_t n_rec;
+    const char *filter_text;              // [SNPGPU_VCF_FILTER_MASKS][SNPGPU_VCF_FILTER_TEXT]
+    char failed_snp_gt;
+    bool preserve_ref_case;
+    uint32_t *len;                        // per record
+    unsigned long long *block_sum, *total;
+    char *out;
+};
+size_t k5_text_blocks(size_t n);
+int    k5_launch_text_sizes(cudaStream_t stream, const K5TextArgs &a);
+int    k5_launch_text_write(cudaStream_t stream, const K5TextArgs &a);
 int    k5_launch_tally(cudaStream_t stream, const uint8_t *text, size_t nbytes, const SiteTable &sites, const CallParams &p,
                        const unsigned long long *offsets, size_t n_rec, snpgpu_vcf_record *rec_out, snpgpu_vcf_alt *alt_out,
                        size_t alt_cap, unsigned long long *alt_count, PileupStatusDev *st, uint8_t *arena, size_t arena_cap);

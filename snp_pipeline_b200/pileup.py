@@ -95,8 +95,14 @@ class Reader(object):
                 ctx.want_vcf_records(vcf_writer is not None)     # (K1 then lists the lines it parses on the way)
                 row, stats = ctx.pileup_consensus(text, sites, params, mode)[:2]
                 if vcf_writer is not None:      # one VCF record per line the reader yields (call_consensus.py:161-184)
-                    records, alts = ctx.pileup_vcf_records(sites, params, mode)
-                    vcf_writer.write_records(text, records, alts, caller, failed_snp_gt)
+                    filter_texts = [";".join(caller.fail_names(m) or ["PASS"]) for m in range(_lib.VCF_FILTER_MASKS)]
+                    if all(len(t) < _lib.VCF_FILTER_TEXT for t in filter_texts):
+                        data_lines, _ = ctx.pileup_vcf_text(sites, params, mode, filter_texts, failed_snp_gt,
+                                                            vcf_writer.preserve_ref_case)
+                        vcf_writer.write_text(data_lines)
+                    else:                               # (filter names longer than the kernel's table: the numbers, formatted here)
+                        records, alts = ctx.pileup_vcf_records(sites, params, mode)
+                        vcf_writer.write_records(text, records, alts, caller, failed_snp_gt)
             except _lib.SnpGpuError as e:
                 raise translate_error(e, self.file_path)
             finally:

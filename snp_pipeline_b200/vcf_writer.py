@@ -95,6 +95,10 @@ class SingleSampleWriter(object):
     def write_header(self, sample_id, filters, reference):
         self.file_handle.write(header_text(sample_id, filters, reference))
 
+    def write_text(self, data_lines):
+        """The records already formatted (Context.pileup_vcf_text: the kernel's K5 text pass)."""
+        self.file_handle.write(data_lines.decode("ascii", "surrogateescape") if isinstance(data_lines, bytes) else data_lines)
+
     def write_records(self, text, records, alts, caller, failed_snp_gt):
         """text: the pileup file's bytes (the chromosome column is copied from it); caller: pileup.ConsensusCaller
         (turns fail masks into the reference's filter names)."""

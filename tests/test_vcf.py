@@ -88,12 +88,17 @@ def _gpu_vcf_body(ctx, text, snps, excl, ps, all_pos, gt=".", preserve=False):
         params = caller.params(ps[0])
         ctx.pileup_consensus(text, sites, params, mode)
         rec, alt = ctx.pileup_vcf_records(sites, params, mode)
+        # the same lines formatted on the device (K5's text pass): what the subcommand writes
+        filter_texts = [";".join(caller.fail_names(m) or ["PASS"]) for m in range(_lib.VCF_FILTER_MASKS)]
+        dev_text, n_dev = ctx.pileup_vcf_text(sites, params, mode, filter_texts, gt, preserve)
     finally:
         sites.close()
     buf = io.StringIO()
     buf.name = "mem.vcf"
     w = vcf_writer.SingleSampleWriter(buf, preserve)
     w.write_records(text, rec, alt, caller, gt)
+    assert n_dev == len(rec)
+    assert dev_text.decode("ascii") == buf.getvalue()
     return buf.getvalue()
 
 
