@@ -832,7 +832,7 @@ def main():
                 vtext, vrec = ctx.pileup_vcf_text(sites_v, w.params, w.lib.MODE_SITES, ftexts)
                 t2 = time.perf_counter()
                 if k:
-                    t_call += t1 - t0; t_vcf += t2 - t1; n_lines += vrec; n_bytes += len(vtext)
+                    t_call += t1 - t0; t_vcf += t2 - t1; n_lines += vrec; n_bytes += int(vtext.size)
             ctx.want_vcf_records(False)
             sites_v.close()
             e2e["production_call"] = {

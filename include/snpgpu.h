@@ -228,7 +228,8 @@ int snpgpu_pileup_vcf_records(snpgpu_ctx *ctx, const snpgpu_sites *sites, const 
  * filter_text: SNPGPU_VCF_FILTER_MASKS NUL-terminated strings of SNPGPU_VCF_FILTER_TEXT bytes each -- the FILTER column of
  * every SNPGPU_FAIL_* mask ("PASS" for 0, else the caller's filter names joined with ';', pileup.py:550-588 /
  * call_consensus.py:165-168); failed_snp_gt: '.', '0' or '1' (--vcfFailedSnpGt); preserve_ref_case: --vcfPreserveRefCase.
- * *n_text = bytes of text (SNPGPU_E_NOMEM when text_cap is smaller: call again with that much room). */
+ * *n_text = bytes of text (SNPGPU_E_NOMEM when text_cap is smaller: the text stays on the device until the next call,
+ * which only copies it when it brings *n_text bytes of room). */
 #define SNPGPU_VCF_FILTER_MASKS 64
 #define SNPGPU_VCF_FILTER_TEXT  64
 int snpgpu_pileup_vcf_text(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snpgpu_params *params, int mode,

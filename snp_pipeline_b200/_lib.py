@@ -380,7 +380,7 @@ class Context(object):
 
     def pileup_vcf_text(self, sites, params, mode, filter_texts, failed_snp_gt=".", preserve_ref_case=False):
         """K5 with the formatting on the device: the data lines of the consensus VCF of the preceding pileup_consensus()
-        call as bytes, and their number.  filter_texts: the FILTER column's text for every fail mask 0 .. 63."""
+        call as a uint8 array, and their number.  filter_texts: the FILTER column's text for every fail mask 0 .. 63."""
         assert len(filter_texts) == VCF_FILTER_MASKS
         table = bytearray(VCF_FILTER_MASKS * VCF_FILTER_TEXT)
         for m, t in enumerate(filter_texts):
@@ -400,7 +400,7 @@ class Context(object):
                 cap = n_text.value
                 continue
             self._check(rc)
-            return out[:n_text.value].tobytes(), n_rec.value
+            return out[:n_text.value], n_rec.value
         raise SnpGpuError(E_NOMEM, "pileup_vcf_text: capacity kept growing")
 
     def pileup_consensus_begin(self, text, sites, params, mode, row_out, line_out=None, stats=None):

@@ -43,6 +43,10 @@ struct snpgpu_ctx {
     DevBuf text, row, lines;                  // staging of the host-buffer entry points
     size_t text_nbytes = 0;                   // bytes of the last text snpgpu_pileup_consensus() staged ...
     bool   text_valid = false;                // ... still there (snpgpu_pileup_vcf_records works on it)
+    size_t vcf_text_bytes = 0;                // formatted data lines kept in vcf_text for a second call with enough room
+    size_t vcf_text_recs = 0;
+    uint64_t vcf_text_key = 0;                // what it was formatted with (the arguments' hash)
+    bool   vcf_text_valid = false;
     bool   want_rec = false;                  // snpgpu_pileup_want_vcf_records: list the parsed lines during the call itself
     bool   rec_valid = false;                 // the last snpgpu_pileup_consensus() left its line list in rec_off ...
     size_t rec_listed = 0;                    // ... this many entries
@@ -580,6 +584,7 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
     bool normalized = false, skip_copy = false;
     ctx->text_valid = false;
+    ctx->vcf_text_valid = false;
     for (int attempt = 0; attempt < 4; attempt++) {
         CK(ctx->text.ensure(nbytes + 64));
         CK(ctx->row.ensure(sites->n_snp + 16));
@@ -633,6 +638,7 @@ int snpgpu_pileup_consensus(snpgpu_ctx *ctx, const void *text, size_t nbytes, co
         if (stats) *stats = hs;
         ctx->text_nbytes = nbytes;
         ctx->text_valid = hs.error_code == 0;
+        ctx->vcf_text_valid = false;
         if (hs.error_code) {
             char msg[160];
             snprintf(msg, sizeof msg, "pileup_consensus: the reference raises (code %d) on the line at byte offset %llu",
@@ -668,6 +674,7 @@ int snpgpu_pileup_consensus_begin(snpgpu_ctx *ctx, const void *text, size_t nbyt
     CK(cudaStreamWaitEvent(st, ctx->lane_event, 0));
     const bool want_lines = mode == SNPGPU_MODE_ALL && line_out != nullptr && line_out_cap > 0;
     L->text_valid = false;
+    L->vcf_text_valid = false;
     CK(L->text.ensure(nbytes + 64));
     CK(L->row.ensure(sites->n_snp + 16));
     CK(L->stats.ensure(sizeof(snpgpu_pileup_stats)));
@@ -832,6 +839,21 @@ int snpgpu_pileup_vcf_text(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snp
         return fail(ctx, SNPGPU_E_ARG, "pileup_vcf_text: null argument");
     size_t n_alt = 0;
     *n_text = 0;
+    uint64_t key = 1469598103934665603ull;                    // FNV-1a over everything the text depends on
+    auto mix = [&key](const void *p, size_t nb) { for (size_t i = 0; i < nb; i++) { key ^= ((const uint8_t *)p)[i]; key *= 1099511628211ull; } };
+    mix(&sites, sizeof sites); mix(params, sizeof *params); mix(&mode, sizeof mode); mix(&failed_snp_gt, sizeof failed_snp_gt);
+    mix(&preserve_ref_case, sizeof preserve_ref_case); mix(filter_text, SNPGPU_VCF_FILTER_MASKS * SNPGPU_VCF_FILTER_TEXT);
+    if (ctx->vcf_text_valid && ctx->vcf_text_key != key) ctx->vcf_text_valid = false;
+    if (ctx->vcf_text_valid) {                                // the call before this one found text_cap too small: the text is still there
+        *n_text = ctx->vcf_text_bytes;
+        *n_rec = ctx->vcf_text_recs;
+        if (ctx->vcf_text_bytes > text_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_text: output capacity too small");
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpyAsync(text_out, ctx->vcf_text.p, ctx->vcf_text_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->vcf_text_valid = false;
+        return SNPGPU_OK;
+    }
     if (int rc = k5_records_dev(ctx, sites, params, mode, 0, n_rec, &n_alt)) return rc;
     const size_t n = *n_rec;
     if (n == 0) return SNPGPU_OK;
@@ -853,11 +875,15 @@ int snpgpu_pileup_vcf_text(snpgpu_ctx *ctx, const snpgpu_sites *sites, const snp
     CK(cudaMemcpyAsync(&total, a.total, sizeof(total), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *n_text = (size_t)total;
-    if (total > text_cap) return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_text: output capacity too small");
     CK(ctx->vcf_text.ensure((size_t)total + 16));
     a.out = (char *)ctx->vcf_text.p;
     ctx->launches += (uint64_t)k5_launch_text_write(st, a);
     CK(cudaGetLastError());
+    if (total > text_cap) {                                   // keep it: the caller comes back with *n_text bytes of room
+        CK(cudaStreamSynchronize(st));
+        ctx->vcf_text_bytes = (size_t)total; ctx->vcf_text_recs = n; ctx->vcf_text_key = key; ctx->vcf_text_valid = true;
+        return fail(ctx, SNPGPU_E_NOMEM, "pileup_vcf_text: output capacity too small");
+    }
     CK(cudaMemcpyAsync(text_out, ctx->vcf_text.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SNPGPU_OK;
@@ -939,6 +965,7 @@ int snpgpu_pileup_depth_sum(snpgpu_ctx *ctx, const void *text, size_t nbytes, in
     if (!ctx || (nbytes && !text) || !sum_out) return fail(ctx, SNPGPU_E_ARG, "pileup_depth_sum: null argument");
     CK(cudaSetDevice(ctx->device));
     ctx->text_valid = false;
+    ctx->vcf_text_valid = false;
     CK(ctx->text.ensure(nbytes + 64));
     if (nbytes) CK(cudaMemcpyAsync(ctx->text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     return snpgpu_pileup_depth_sum_dev(ctx, ctx->text.p, nbytes, sum_out, lines_out, error_offset);

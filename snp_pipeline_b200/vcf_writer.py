@@ -97,7 +97,12 @@ class SingleSampleWriter(object):
 
     def write_text(self, data_lines):
         """The records already formatted (Context.pileup_vcf_text: the kernel's K5 text pass)."""
-        self.file_handle.write(data_lines.decode("ascii", "surrogateescape") if isinstance(data_lines, bytes) else data_lines)
+        raw = getattr(self.file_handle, "buffer", None)
+        if raw is not None:                             # a text file: the bytes go straight to its binary layer
+            self.file_handle.flush()
+            raw.write(memoryview(data_lines))
+        else:                                           # (a StringIO in the tests)
+            self.file_handle.write(bytes(data_lines).decode("ascii", "surrogateescape"))
 
     def write_records(self, text, records, alts, caller, failed_snp_gt):
         """text: the pileup file's bytes (the chromosome column is copied from it); caller: pileup.ConsensusCaller

@@ -98,7 +98,7 @@ def _gpu_vcf_body(ctx, text, snps, excl, ps, all_pos, gt=".", preserve=False):
     w = vcf_writer.SingleSampleWriter(buf, preserve)
     w.write_records(text, rec, alt, caller, gt)
     assert n_dev == len(rec)
-    assert dev_text.decode("ascii") == buf.getvalue()
+    assert dev_text.tobytes().decode("ascii") == buf.getvalue()
     return buf.getvalue()
 
 
