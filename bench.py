@@ -177,7 +177,7 @@ def device_step(w, dist, world):
     # the merged list never leaves HBM: K2's sorted unique keys -> the table K1 probes (snpgpu_sites_create_from_keys_dev)
     sites = w.lib.Sites.from_keys_dev(ctx, [CONTIG], [w.args.genome_len], local.data_ptr(), n_uniq)
     matrix = torch.empty((w.n, (max(n_uniq, 1) + 63) // 64 * 64), dtype=torch.uint8, device="cuda")    # 16-byte aligned rows
-    # one launch sequence per 16 samples (snpgpu_pileup_consensus_batch_dev); every sample has its own per-line results
+    # one launch sequence per <= 64 samples (snpgpu_pileup_consensus_batch_dev); every sample has its own per-line results
     ctx.pileup_consensus_batch_dev([(w.texts[i].data_ptr(), w.nbytes[i], matrix[i].data_ptr(), w.lines_dev[i].data_ptr(),
                                      w.args.genome_len + 64, w.stats_dev[i].data_ptr()) for i in range(w.n)],
                                    sites, w.params, w.lib.MODE_ALL)
@@ -756,7 +756,7 @@ def main():
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650",
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n,
-                "launch_unit": "one sample (a launch of k1_pileup_kernel + k1_rest_kernel covers a batch of up to 16 "
+                "launch_unit": "one sample (a launch of k1_pileup_kernel + k1_rest_kernel covers a batch of up to 64 "
                                "samples; its time is divided by the samples it covered)",
                 "share_of_step": k1_ms / ms if ms else None,
                 "k4": {"avg_launch_ms": k4_ms / max(k4_n, 1), "pair_sites_per_s":

@@ -71,7 +71,7 @@ uint64_t    snpgpu_launch_count(const snpgpu_ctx *ctx);
 /* Per-kernel device timing (bench.py's roofline): when enabled, every launch of the named kernel is bracketed by
  * CUDA events on the context's stream.  snpgpu_kernel_time synchronises the stream, returns the summed device time
  * and the number of launches since the last call, and resets both. */
-#define SNPGPU_KERNEL_PILEUP   0   /* k1_pileup_kernel + k1_rest_kernel (one pair per batch of up to 16 samples) */
+#define SNPGPU_KERNEL_PILEUP   0   /* k1_pileup_kernel + k1_rest_kernel (one pair per batch of up to 64 samples) */
 #define SNPGPU_KERNEL_DISTANCE 1   /* k4_pairs_kernel (+ its pack kernel) */
 int         snpgpu_enable_timing(snpgpu_ctx *ctx, int on);
 int         snpgpu_kernel_time(snpgpu_ctx *ctx, int kernel, double *ms_out, uint64_t *launches_out);
@@ -164,7 +164,7 @@ int snpgpu_pileup_consensus_dev(snpgpu_ctx *ctx, const void *text_dev, size_t nb
                                 snpgpu_pileup_stats *stats_dev);
 
 /* The same for a batch of samples that share the site table and the parameters (the reference runs one call_consensus
- * process per sample, run.py:709-710): one launch sequence per 16 samples, so the fixed costs of a launch (its tail, the
+ * process per sample, run.py:709-710): one launch sequence per up to 64 samples (split evenly), so the fixed costs of a launch (its tail, the
  * small kernels around it) are paid once per batch.  samples: host array; every pointer in it is a device pointer with
  * the meaning it has in snpgpu_pileup_consensus_dev.  Nothing is synchronised. */
 typedef struct {

@@ -429,7 +429,7 @@ class Context(object):
 
     def pileup_consensus_batch_dev(self, samples, sites, params, mode):
         """Batch form of pileup_consensus_dev: samples = sequence of (text_ptr, nbytes, row_ptr, line_ptr, line_cap,
-        stats_ptr) tuples of device pointers (0 = none), or a ready (PileupSample * n) array.  One launch sequence per 16
+        stats_ptr) tuples of device pointers (0 = none), or a ready (PileupSample * n) array.  One launch sequence per up to 64
         samples; nothing is synchronised."""
         if isinstance(samples, ctypes.Array):
             arr = samples

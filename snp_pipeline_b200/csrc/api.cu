@@ -540,9 +540,14 @@ int snpgpu_pileup_consensus_batch_dev(snpgpu_ctx *ctx, const snpgpu_pileup_sampl
     int rc = k1_check(ctx, samples, n_samples, sites, params, mode);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    for (size_t i = 0; i < n_samples; i += K1_BATCH) {
-        rc = k1_run_batch(ctx, samples + i, std::min<size_t>(K1_BATCH, n_samples - i), sites, params, mode, nullptr, nullptr, 0);
+    // launches of equal size (a launch's fixed cost -- the pileup kernel's last tiles, the follow-up kernel's latency -- is
+    // shared by the samples it covers: 100 samples go as 50 + 50, not 64 + 36)
+    const size_t n_launch = (n_samples + K1_BATCH - 1) / K1_BATCH;
+    for (size_t b = 0, i = 0; b < n_launch; b++) {
+        const size_t take = (n_samples - i + (n_launch - b) - 1) / (n_launch - b);
+        rc = k1_run_batch(ctx, samples + i, take, sites, params, mode, nullptr, nullptr, 0);
         if (rc) return rc;
+        i += take;
     }
     return SNPGPU_OK;
 }

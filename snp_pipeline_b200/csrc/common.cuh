@@ -43,7 +43,10 @@ constexpr int K1_PAD         = 32;                   // '\n' sentinels after the
 constexpr int K1_LCAP        = 8;                    // per-line results a lane keeps in the staging array per tile (more -> overflow list)
 constexpr int K1_ORDER_TILES = 512;                  // tiles per group of the ordering pass (k1_tile_prefix_kernel)
 constexpr int K1_NAMEW       = 16;                   // words of the expected contig's name a warp keeps in shared memory
-constexpr int K1_BATCH       = 16;                   // samples one launch of the pileup kernel takes (the descriptors are kernel parameters)
+#ifndef K1_CFG_BATCH
+#define K1_CFG_BATCH 64
+#endif
+constexpr int K1_BATCH       = K1_CFG_BATCH;         // samples one launch of the pileup kernel takes (the descriptors are kernel parameters: 10 KB of the 32 KB)
 static_assert(K1_LANE_BYTES % 16 == 0 && K1_LANE_BYTES <= 1008 && K1_WIN % 16 == 0, "tile geometry");
 
 // What the second / third parser tiers (line_fast.cuh, line_general.cuh) see of one sample: built per line by the
@@ -112,7 +115,7 @@ struct K1Batch {
     SiteTable           sites;
     CallParams          p;
 };
-static_assert(sizeof(K1Batch) <= 4000, "the batch descriptor travels as a kernel parameter");
+static_assert(sizeof(K1Batch) <= 32000, "the batch descriptor travels as a kernel parameter (32 764 bytes at most since CUDA 12.1)");
 
 // ---- PTX: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

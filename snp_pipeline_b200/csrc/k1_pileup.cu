@@ -623,8 +623,11 @@ int k1_launch(cudaStream_t stream, const K1Batch &g, int grid_blocks, int n_sms)
     const size_t sh = k1_smem_bytes();
     if (g.mode == SNPGPU_MODE_ALL) k1_pileup_kernel<true><<<grid, K1_THREADS, sh, stream>>>(g);
     else k1_pileup_kernel<false><<<grid, K1_THREADS, sh, stream>>>(g);
-    if (g.has_qual) k1_rest_kernel<true><<<n_sms * 8, 128, 0, stream>>>(g);
-    else k1_rest_kernel<false><<<n_sms * 8, 128, 0, stream>>>(g);
+#ifndef K1_REST_BLOCKS
+#define K1_REST_BLOCKS 8
+#endif
+    if (g.has_qual) k1_rest_kernel<true><<<n_sms * K1_REST_BLOCKS, 128, 0, stream>>>(g);
+    else k1_rest_kernel<false><<<n_sms * K1_REST_BLOCKS, 128, 0, stream>>>(g);
     return 2;
 }
 
