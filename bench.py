@@ -209,6 +209,7 @@ def host_step(w, pool, pool_n, bufs, dist=None, world=1):
     than one rank the two exchange steps of device_step() happen here too, from and to host memory."""
     from snp_pipeline_b200 import sharding
     torch, ctx, lib = w.torch, w.ctx, w.lib
+    t_0 = time.perf_counter()
     uniq, cnt, samples = ctx.merge_sites(w.keys_host, w.samp_host)
     h2d = w.keys_host.nbytes + w.samp_host.nbytes
     d2h = uniq.nbytes + cnt.nbytes + samples.nbytes
@@ -220,14 +221,18 @@ def host_step(w, pool, pool_n, bufs, dist=None, world=1):
         h2d += uniq.nbytes + allkeys.nbytes + owner.nbytes
         uniq, cnt, samples = ctx.merge_sites(allkeys, owner)
         d2h += allkeys.nbytes + uniq.nbytes + cnt.nbytes + samples.nbytes
+    t_1 = time.perf_counter()
     sites = build_sites(ctx, uniq)
+    t_2 = time.perf_counter()
     n_sites = uniq.size
     rows, lines, stats = bufs
     # one call kept ahead (snpgpu_pileup_consensus_begin / _end): sample i+1's text crosses PCIe while sample i's
     # kernels run and its results come back
     in_flight = None
+    worst = (0.0, -1, "")
     for i in range(w.n + 1):
         nxt = None
+        t_b = time.perf_counter()
         if i < w.n:
             k = i % len(pool)
             slot = ctypes.c_int(-1)
@@ -238,10 +243,17 @@ def host_step(w, pool, pool_n, bufs, dist=None, world=1):
             ctx._check(rc)
             h2d += pool_n[k]
             nxt = (slot.value, i % 2)
+        t_m = time.perf_counter()
         if in_flight is not None:
             ctx._check(ctx.lib.snpgpu_pileup_consensus_end(ctx.handle, in_flight[0]))
             d2h += n_sites + 2 * stats[in_flight[1]].n_lines + ctypes.sizeof(stats[0])
+        t_e = time.perf_counter()
+        if t_m - t_b > worst[0]:
+            worst = (t_m - t_b, i, "begin")
+        if t_e - t_m > worst[0]:
+            worst = (t_e - t_m, i, "end")
         in_flight = nxt
+    t_3 = time.perf_counter()
     m = rows[:, :n_sites]
     if world == 1:
         d = np.zeros((w.n, w.n), dtype=np.int32)
@@ -258,7 +270,13 @@ def host_step(w, pool, pool_n, bufs, dist=None, world=1):
         d = dd.cpu().numpy()
         h2d += rows.nbytes
         d2h += d.nbytes
+    t_4 = time.perf_counter()
     sites.close()
+    w.e2e_breakdown = {"merge_sites_ms": (t_1 - t_0) * 1e3, "site_table_ms": (t_2 - t_1) * 1e3,
+                       "pileup_calls_ms": (t_3 - t_2) * 1e3, "distance_ms": (t_4 - t_3) * 1e3,
+                       "site_table_free_ms": (time.perf_counter() - t_4) * 1e3,
+                       "slowest_call": {"ms": worst[0] * 1e3, "sample": worst[1], "which": worst[2]}}
+    w.e2e_all = getattr(w, "e2e_all", []) + [w.e2e_breakdown]
     return m, d, h2d, d2h
 
 
@@ -801,8 +819,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
+        step_ms = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             m, dd, h2d, d2h = host_step(w, pool, pool_n, bufs, dist, world)
+            step_ms.append((time.perf_counter() - ts) * 1e3)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -813,7 +834,7 @@ def main():
             assert m[k].tobytes() == matrix_host[k % len(pool)].tobytes(), "e2e row differs from the device-resident row"
         e2e = {"value": positions / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "h2d_gbs": h2d / e2e_s / 1e9}
+               "h2d_gbs": h2d / e2e_s / 1e9, "step_breakdown": getattr(w, "e2e_all", [])[-e2e_steps:], "step_ms": step_ms}
         # ---- the per-sample call the reference's run.py:709 makes: default mode + consensus.vcf (K1 sites mode, then K5:
         #      sort of the parsed lines' offsets, tallies, the data lines' text on the device), host buffers, N = 1 only
         if world == 1:

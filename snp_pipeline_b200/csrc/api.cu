@@ -102,7 +102,7 @@ struct snpgpu_sites {
     int n_contigs = 0;
     void *blob = nullptr;                     // one device allocation holding every array below
     size_t blob_bytes = 0;
-    bool pooled = false;                      // built by snpgpu_sites_create_from_keys_dev: the blob goes back to the context
+    bool pooled = false;                      // the blob goes back to the context's pool when the table is destroyed
     SiteTable table;                          // device pointers
     int32_t *snp_unique = nullptr;            // device, n_snp: unique-site index of snplist entry k
 };
@@ -266,8 +266,23 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
     size_t s_q3 = add(h.q3rows.data(), h.q3rows.size() * 4);
     snpgpu_sites *s = new (std::nothrow) snpgpu_sites();
     if (!s) return fail(ctx, SNPGPU_E_NOMEM, "sites_create: host allocation");
-    cudaError_t e = cudaMalloc(&s->blob, total);
-    if (e != cudaSuccess) { delete s; return fail(ctx, SNPGPU_E_NOMEM, "sites_create: cudaMalloc", e); }
+    // the blob of a destroyed table when one is large enough (cudaFree stalls the whole device -- up to hundreds of
+    // milliseconds next to page-locked copies -- so a loop that builds a table per batch must not free one per batch)
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < ctx->sites_pool.size(); k++) {
+        if (ctx->sites_pool[k].second >= total) {
+            s->blob = ctx->sites_pool[k].first; s->blob_bytes = ctx->sites_pool[k].second;
+            ctx->sites_pool.erase(ctx->sites_pool.begin() + (long)k);
+            break;
+        }
+    }
+    if (!s->blob) {
+        const size_t want = (total + (total >> 3) + 4095) & ~(size_t)4095;
+        e = cudaMalloc(&s->blob, want);
+        if (e != cudaSuccess) { delete s; return fail(ctx, SNPGPU_E_NOMEM, "sites_create: cudaMalloc", e); }
+        s->blob_bytes = want;
+    }
+    s->pooled = true;
     for (const Sec &x : secs) {
         if (!x.bytes || !x.src) continue;
         e = cudaMemcpyAsync((uint8_t *)s->blob + x.off, x.src, x.bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -292,7 +307,8 @@ int snpgpu_sites_create(snpgpu_ctx *ctx, const char *contig_names, const int32_t
 
 void snpgpu_sites_destroy(snpgpu_sites *sites) {
     if (!sites) return;
-    if (sites->pooled && sites->ctx && sites->blob && sites->ctx->sites_pool.size() < 4) {
+    if (sites->pooled && sites->ctx && sites->blob && sites->ctx->sites_pool.size() < 4 && !sites->ctx->pending[0].active &&
+        !sites->ctx->pending[1].active) {
         // whatever still reads the table was enqueued on the context's stream, and so is whatever reuses the blob
         sites->ctx->sites_pool.emplace_back(sites->blob, sites->blob_bytes);
         delete sites;
