@@ -98,10 +98,22 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
                         SiteWord sw{0u, 0u, 0u, 0u};
                         if (known) sw = t.words[widx];
                         st = q3_rest(m, q3.after, (uint32_t)nbytes, *p, 1u, &q3);
+                        bool second = st == ST_DETAIL;                   // the follow-up kernel's second look: indel tokens skipped
                         if (st == ST_TALLY) {                            // well-formed, only the call is left: queued with its end known
                             if (q3.end != e) { counters[3] = s; counters[4] = 94; break; }   // harness self-check: that end
                             st = ST_DETAIL;
-                        } else if (st == ST_DETAIL) {                    // the follow-up kernel's second look: indel tokens skipped
+                        } else if (st == ST_SIGN) {                      // the pileup kernel looks for the line end from the quality column on
+                            uint32_t odd2 = 0;
+                            if (q3_find_nl(m, q3.end, 1u, &odd2) != e) { counters[3] = s; counters[4] = 93; break; }   // harness self-check
+                            bool odd_q = false, odd_f = false;
+                            for (size_t x = q3.end; x < e; x++) odd_q |= (buf[x] >= 0x0b && buf[x] <= 0x0d) || buf[x] >= 0x80;
+                            if (odd_q && !odd2) { counters[3] = s; counters[4] = 92; break; }
+                            for (size_t x = s; x < q3.end; x++) odd_f |= (buf[x] < 0x21 && buf[x] != '\t') || buf[x] >= 0x80;
+                            if (odd_f) { counters[3] = s; counters[4] = 91; break; }         // ... having seen nothing odd in front of it
+                            st = ST_DETAIL;
+                            second = true;
+                        }
+                        if (second) {
                             st = q3_rest<true>(m, q3.after, (uint32_t)e, *p, 1u, &q3);
                             if (st == ST_OK && q3.end != e) st = ST_DETAIL;
                             if (st == ST_TALLY) st = ST_DETAIL;

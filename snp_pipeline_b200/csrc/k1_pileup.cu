@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         next = q.end + 1u;
                     } else {
                         uint32_t odd = 0;
-                        const uint32_t e = q3_find_nl(m, s, one, &odd);
+                        const uint32_t e = q3_find_nl(m, st == ST_SIGN ? q.end : s, one, &odd);   // (ST_SIGN: columns 1-5 are clean)
                         push = true;
                         push_len = e < wlen || eof ? e - s : 0u;
                         push_flag = odd ? 1u : 0u;

@@ -19,8 +19,8 @@
 // row(word) / row4(word, out[4]) for the cached contig's name rows, tab16(i) for the filter tables: the warp's slice of
 // shared memory in the pileup kernel, the text in global memory + tables in shared memory in its follow-up kernel, plain
 // arrays in tests/cpu_sim -- aligned loads only, 32-bit addressing, and the compiler always knows the address space.  Preconditions: '\n' sentinels in bytes
-// [limit, limit + QUICK_PAD) of the window.  Any byte values are safe: every word that takes part in a SWAR test is OR-ed
-// into a guard, and a byte >= 0x80 declines the line.
+// [limit, limit + QUICK_PAD) of the window.  Any byte values are safe: a byte >= 0x80 ends the column it stands in like a
+// separator would (Q3_LOW; the key columns and the quality column test for it directly), and the line is declined.
 #pragma once
 #include "line_fast.cuh"
 
@@ -29,6 +29,9 @@ namespace snpgpu {
 enum : int { ST_DETAIL = 67 };         // "not for this tier": the line goes to the follow-up kernel, no side effects
 enum : int { ST_TALLY = 68 };          // declined like ST_DETAIL, but the line is well-formed and out->end is its '\n':
                                        // only the call needs the per-letter tallies of the second tier
+enum : int { ST_SIGN = 69 };           // declined like ST_DETAIL by the first look (INDEL = false) over a '+' / '-' / ')' / '/' in
+                                       // the bases column -- an indel token, as a rule: columns 1-5 hold no separator but
+                                       // their tabs and no byte >= 0x80, out->end is the first byte of the quality column
 constexpr uint32_t QUICK_PAD = 32;     // '\n' sentinels the caller keeps behind `limit` (word over-reads land there)
 
 // acc + 128 * (number of bytes of `flags` that are 0x80); flags holds 0x80 / 0x00 bytes only
@@ -221,20 +224,34 @@ SNP_HD bool q3_key(const M &m, uint32_t s, uint32_t limit, const Q3Contig &cc, u
 #ifndef Q3_LOOPN
 #define Q3_LOOPN 4            // words of the bases column per trip of the first tier's loop
 #endif
-// one whole word of the bases column (no separator in it): classes, anomalies, counts
+// acc | (a & b), as ONE three-input logic instruction (the compiler splits it in two in half of the unrolled copies)
+SNP_HD uint32_t or_and(uint32_t acc, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
+    return r;
+#else
+    return acc | (a & b);
+#endif
+}
+// bit 7 <-> byte < 0x21 or byte >= 0x80.  The LOWEST flag of a word is exact whatever the bytes above it are (a byte
+// >= 0xa1 carries into its upper neighbour, never downwards), and a word without a flag holds bytes 0x21..0x7f only: the
+// SWAR tests below never see a byte that could carry.
+#define Q3_LOW(w) ((Q3_NADD(0x5f5f5f5fu, w) | (w)) & H)
+// one whole word of the bases column (no separator in it, bytes 0x21..0x7f): classes, anomalies, counts.  car / part /
+// prevcar carry noise below bit 7 of every byte; whatever counts with them is masked with H.
 #define Q3_BASES_WORD(w) do { \
-        guard |= w; \
-        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & H; \
+        const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w); \
         const uint32_t part = funnel_l8(prevcar, car); \
-        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & H; \
+        const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w); \
         const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu); \
         const uint32_t dck = ~(y2 | part) & H; \
         const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u); \
         const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb); \
         an0 |= ~(y3 | part); \
         an1 |= ~(yr | part); \
-        an2 |= car & part; \
-        a_rem = flag_sum(car | part | dol, a_rem); \
+        an2 = or_and(an2, car, part); \
+        a_rem = flag_sum((car | part | dol) & H, a_rem); \
         a_dc = flag_sum(dck, a_dc); \
         a_dot = flag_weigh(w, dck, a_dot); \
         prevcar = car; \
@@ -278,14 +295,14 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         w = (w & mk) | (0x30303030u & ~mk);
     }
     uint32_t a_rem = 0, a_dc = 0, a_dot = 0;               // 128 x (removed bytes, kept '.'/',', sum of the kept '.'/',' bytes)
-    uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0, guard = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
+    uint32_t an0 = 0, an1 = 0, an2 = 0, prevcar = 0;     // anomaly flags (bit 7 of a byte; other bits: noise)
     uint32_t low;
     uint32_t wn = 0, wn2 = 0, wn3 = 0;                     // the words behind w, asked for a trip ahead (first look only)
     if constexpr (Q3_LOOPN > 1 && !INDEL) wn = m.ld(k + 1u);
     if constexpr (Q3_LOOPN > 2 && !INDEL) wn2 = m.ld(k + 2u);
     if constexpr (Q3_LOOPN > 3 && !INDEL) wn3 = m.ld(k + 3u);
     for (;;) {
-        low = Q3_NADD(0x5f5f5f5fu, w) & H;                 // bit 7 <-> byte < 0x21
+        low = Q3_LOW(w);                                   // bit 7 <-> byte < 0x21 (or >= 0x80): the column ends here
         if (INDEL) {
             const uint32_t first = low & (0u - low);
             const uint32_t valid = low ? (first - 1u) & H : H;                                 // the column's bytes of this word
@@ -299,7 +316,6 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
                 const uint32_t ch = (w >> (8u * sb)) & 0xffu;
                 if (ch != '+' && ch != '-') return ST_DETAIL;
                 const uint32_t v2 = (fs - 1u) & H;                                               // the bytes in front of the sign
-                guard |= w & v2;
                 const uint32_t car2 = car & v2, part2 = part & v2;
                 const uint32_t dol2 = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & v2;
                 const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);
@@ -330,7 +346,7 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         if (low) break;
         if constexpr (Q3_LOOPN > 1 && !INDEL) {            // several words a trip, each left as soon as it holds the separator:
             Q3_BASES_WORD(w);                              // the later words' loads have whole words' work to arrive
-#define Q3_NEXT_WORD(x) w = (x); ++k; low = Q3_NADD(0x5f5f5f5fu, w) & H; if (low) break; Q3_BASES_WORD(w)
+#define Q3_NEXT_WORD(x) w = (x); ++k; low = Q3_LOW(w); if (low) break; Q3_BASES_WORD(w)
             Q3_NEXT_WORD(wn);
             if constexpr (Q3_LOOPN > 2) { Q3_NEXT_WORD(wn2); }
             if constexpr (Q3_LOOPN > 3) { Q3_NEXT_WORD(wn3); }
@@ -345,12 +361,12 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         }
     }
     uint32_t q0;
+    bool sep_tab;
     const uint32_t qw1 = m.ld(k + 1u), qw2 = m.ld(k + 2u); // the quality column starts in this word or the next: asked for now
     {   // the word that holds the separator: the same, restricted to the bytes in front of it
         const uint32_t first = low & (0u - low);
         const uint32_t valid = (first - 1u) & H;
         const uint32_t j = (uint32_t)ctz32(first) >> 3;
-        guard |= w & valid;                                // (only the bytes in front of the separator)
         const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & valid;
         const uint32_t part = funnel_l8(prevcar, car);                     // may reach the separator itself
         const uint32_t dol = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & valid;
@@ -364,11 +380,14 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
         a_rem = flag_sum((car | part | dol) & valid, a_rem);
         a_dc = flag_sum(dck, a_dc);
         a_dot = flag_weigh(w, dck, a_dot);
-        if (((w >> (8u * j)) & 0xffu) != '\t') an2 |= H;                   // the column ends in a tab
+        sep_tab = ((w >> (8u * j)) & 0xffu) == '\t';                       // the column ends in a tab
         q0 = 4u * k + j + 1u;
     }
     const uint32_t bases_len = q0 - 1u - b0;
-    if (((an0 | an1 | an2 | guard) & H) != 0u || bases_len == 0u) return ST_DETAIL;
+    if (((an0 | an1 | an2) & H) != 0u || !sep_tab || bases_len == 0u) {
+        if (!INDEL && sep_tab && (an0 & H) != 0u) { out->end = q0; return ST_SIGN; }
+        return ST_DETAIL;
+    }
     const uint32_t nb = bases_len - (a_rem >> 7);          // length of the stripped string
     const uint32_t qe = q0 + nb;                           // where the line has to end
     if (nb < 1u || qe > limit) return ST_DETAIL;

@@ -314,3 +314,24 @@ def test_indel_token_corners(sim, seed):
     for all_pos in (False, True):
         c = _compare(sim, text, snps, [], ps, all_pos)
         assert c[0] == (len(good) if all_pos else c[0])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_odd_bytes_in_columns(sim, seed):
+    """Bytes >= 0x80 (with and without a SWAR carry into their neighbour: 0xa0 / 0xa1), DEL, blanks and control bytes
+    dropped into the name, depth, bases and quality columns of otherwise realistic lines: the first tier has to end the
+    column there and decline; the result (the domain error included) is the oracle's."""
+    for sub in range(60):
+        rng = random.Random(1000 * seed + sub)
+        lines = [linegen.realistic_line(rng, 1 + k, indel_rate=rng.choice([0.0, 0.05])).encode("latin-1") for k in range(12)]
+        k = rng.randrange(len(lines))
+        f = lines[k].split(b"\t")
+        col = rng.choice([4, 4, 4, 5, 1, 0])
+        b = bytearray(f[col])
+        for _ in range(rng.choice([1, 1, 2])):
+            b[rng.randrange(len(b))] = rng.choice([0x80, 0x81, 0xa0, 0xa1, 0xa2, 0xde, 0xdf, 0xe0, 0xff, 0x7f, 0x20, 0x1f,
+                                                   0x0b, 0x0c, 0x1c, 0x00])
+        f[col] = bytes(b)
+        lines[k] = b"\t".join(f)
+        for all_pos in (True, False):
+            _compare(sim, b"".join(lines), [(linegen.CHROM, 1 + k)], [], PARAM_SETS[sub % len(PARAM_SETS)], all_pos)
