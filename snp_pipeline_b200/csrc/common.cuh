@@ -158,7 +158,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // warp-aggregated form, which shuffles the result out right away and so waits for it
 __device__ __forceinline__ uint32_t atom_inc_u32(unsigned int *p) {
     uint32_t old;
-    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    // (inc, not add: ptxas turns an add at a uniform address into a warp-aggregated one whose result is shuffled out -- and
+    //  so waited for -- on the spot; the ticket is wanted a whole tile later)
+    asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "l"(p) : "memory");
     return old;
 }
 
