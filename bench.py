@@ -767,7 +767,8 @@ def main():
     achieved = alg_bytes / (k1_avg_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        # (the ncu capture ran a batch of two samples: per sample, the unit `achieved` and `alg_bytes_per_launch` use)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_sample")
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "kernel": "k1_pileup_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

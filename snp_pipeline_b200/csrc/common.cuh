@@ -141,7 +141,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // waits with a short sleep between polls, so that a waiting warp leaves the issue slots to the others
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+#ifndef K1_CFG_SLEEP
+#define K1_CFG_SLEEP 200
+#endif
+    while (!mbar_try_wait(bar, parity)) { if (K1_CFG_SLEEP) __nanosleep(K1_CFG_SLEEP); }
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
             fence_proxy_async();
             mbar_arrive_expect_tx(bar, bulk);
             bulk_g2s(buf, text + base, bulk, bar);
-            const unsigned long long nbase = base + (unsigned long long)n_gwarps * TILE;   // about one round from now -> L2
+#ifndef K1_CFG_PF_ROUNDS
+#define K1_CFG_PF_ROUNDS 1
+#endif
+            const unsigned long long nbase = base + (unsigned long long)(K1_CFG_PF_ROUNDS * n_gwarps) * TILE;   // about one round from now -> L2
             if (nbase < nbytes) {
                 const unsigned long long nleft = nbytes - nbase;
                 const uint32_t nb = (nleft < (unsigned long long)WIN ? (uint32_t)nleft : WIN) & ~15u;
