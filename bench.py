@@ -355,10 +355,8 @@ def run_reference(args, rank):
     """--impl reference: the CPU restatement of the reference's path with every host thread, bounded sample."""
     if rank != 0:
         return
-    import torch
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
-    from snp_pipeline_b200 import _lib
     orc.build()
     orc.lib()
     cores = os.cpu_count() or 1
@@ -367,17 +365,11 @@ def run_reference(args, rank):
     except AttributeError:
         pass
     n_ref = max(1, min(cores, 32, args.samples))             # one sample per host thread (32 x 0.46 GB of text at most)
-    ctx = _lib.Context(0)
-    cap = args.genome_len * 112 + 4096
-    scratch = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    texts, site_pos = [], []
-    for i in range(n_ref):
-        spec = _lib.SynthSpec(SEED, i, args.genome_len, 24, args.pool_sites, args.carry, 0.0)
-        nb = ctx.synth_pileup_dev(spec, CONTIG, scratch.data_ptr(), cap)
-        texts.append(scratch[:nb].cpu().numpy().copy())
-        site_pos.append(ctx.synth_sample_sites(spec))
-    del scratch
-    ctx.close()
+    # the inputs: the same synthetic samples the GPU arm parses, written on the host by the generator's own line function
+    # (oracle/synth_host.cpp) -- this arm loads neither torch nor libsnpgpu.so
+    texts = [orc.synth_pileup(SEED, i, args.genome_len, 24, args.pool_sites, args.carry, 0.0, CONTIG, threads=cores)
+             for i in range(n_ref)]
+    site_pos = [orc.synth_sample_sites(SEED, i, args.genome_len, 24, args.pool_sites, args.carry) for i in range(n_ref)]
     keys = np.concatenate([p.astype(np.uint64) for p in site_pos])
     samp = np.concatenate([np.full(p.size, i, dtype=np.uint32) for i, p in enumerate(site_pos)])
 

@@ -63,6 +63,65 @@ def build(force=False):
     return _SO
 
 
+# ---- the bench's synthetic input written on the host (oracle/synth_host.cpp: the generator's own line function,
+#      snp_pipeline_b200/csrc/synth_line.cuh, compiled for the host -- bench.py --impl reference must not load the GPU library)
+_SYNTH_SRC = os.path.join(_HERE, "synth_host.cpp")
+_SYNTH_HDRS = [os.path.join(_HERE, "..", "snp_pipeline_b200", "csrc", n) for n in ("synth_line.cuh", "hd.cuh")]
+_SYNTH_SO = os.path.join(_BUILD, "libsynthhost.so")
+_synth = None
+
+
+class SynthSpec(ctypes.Structure):                           # = snpgpu_synth_spec (include/snpgpu.h)
+    _fields_ = [("seed", ctypes.c_uint64), ("sample", ctypes.c_uint32), ("genome_len", ctypes.c_uint32),
+                ("mean_depth", ctypes.c_uint32), ("n_pool_sites", ctypes.c_uint32),
+                ("site_carry_prob", ctypes.c_float), ("indel_line_rate", ctypes.c_float)]
+
+
+def build_synth(force=False):
+    """Compile synth_host.cpp (g++ -O2).  Returns the path of the shared object."""
+    srcs = [_SYNTH_SRC] + [h for h in _SYNTH_HDRS if os.path.exists(h)]
+    if force or not os.path.exists(_SYNTH_SO) or os.path.getmtime(_SYNTH_SO) < max(os.path.getmtime(s) for s in srcs):
+        os.makedirs(_BUILD, exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", _SYNTH_SO, _SYNTH_SRC])
+    return _SYNTH_SO
+
+
+def _synth_lib():
+    global _synth
+    if _synth is None:
+        L = ctypes.CDLL(build_synth())
+        L.synth_host_pileup.restype = ctypes.c_ulonglong
+        L.synth_host_pileup.argtypes = [ctypes.POINTER(SynthSpec), ctypes.c_char_p, ctypes.c_void_p, ctypes.c_ulonglong,
+                                        ctypes.c_int]
+        L.synth_host_sites.restype = ctypes.c_ulonglong
+        L.synth_host_sites.argtypes = [ctypes.POINTER(SynthSpec), ctypes.c_void_p, ctypes.c_ulonglong]
+        _synth = L
+    return _synth
+
+
+def synth_pileup(seed, sample, genome_len, mean_depth, n_pool_sites, carry, indel_rate, contig, threads=8):
+    """One synthetic sample's pileup text as a uint8 array: the bytes snpgpu_synth_pileup_dev writes for the same spec."""
+    L = _synth_lib()
+    spec = SynthSpec(seed, sample, genome_len, mean_depth, n_pool_sites, carry, indel_rate)
+    cap = genome_len * 112 + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    n = L.synth_host_pileup(ctypes.byref(spec), contig.encode(), out.ctypes.data, cap, threads)
+    if n > cap:
+        out = np.empty(n, dtype=np.uint8)
+        n = L.synth_host_pileup(ctypes.byref(spec), contig.encode(), out.ctypes.data, n, threads)
+    return out[:n].copy()
+
+
+def synth_sample_sites(seed, sample, genome_len, mean_depth, n_pool_sites, carry):
+    """1-based positions of the pool sites the sample carries, ascending (uint32)."""
+    L = _synth_lib()
+    spec = SynthSpec(seed, sample, genome_len, mean_depth, n_pool_sites, carry, 0.0)
+    n = L.synth_host_sites(ctypes.byref(spec), None, 0)
+    out = np.empty(max(int(n), 1), dtype=np.uint32)
+    L.synth_host_sites(ctypes.byref(spec), out.ctypes.data, n)
+    return out[:int(n)]
+
+
 _lib = None
 
 

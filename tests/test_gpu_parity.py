@@ -320,6 +320,23 @@ def _synth(ctx, genome_len, sample, pool, carry=0.05, seed=20261017):
     return spec, buf, n
 
 
+@pytest.mark.parametrize("genome_len,sample,indel", [(150000, 0, 0.0), (60000, 5, 0.05)])
+def test_synthetic_text_host_generator(ctx, genome_len, sample, indel):
+    """The reference arm of bench.py parses inputs written on the host (oracle/synth_host.cpp, the generator's own line
+    function compiled with g++): they are the bytes the device generator writes, and so are the carried sites."""
+    from snp_pipeline_b200 import _lib
+    import torch
+    spec = _lib.SynthSpec(20261017, sample, genome_len, 24, genome_len // 100, 0.05, indel)
+    cap = genome_len * 112 + 4096
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    chrom = "gi|0000000|ref|SYN_5000K.1|"
+    n = ctx.synth_pileup_dev(spec, chrom, buf.data_ptr(), cap)
+    host = orc.synth_pileup(20261017, sample, genome_len, 24, genome_len // 100, 0.05, indel, chrom, threads=3)
+    assert host.size == n and np.array_equal(host, buf[:n].cpu().numpy())
+    assert np.array_equal(orc.synth_sample_sites(20261017, sample, genome_len, 24, genome_len // 100, 0.05),
+                          ctx.synth_sample_sites(spec))
+
+
 @pytest.mark.parametrize("genome_len,sample", [(200000, 0), (5000000, 3)])
 def test_synthetic_sample_device_resident(ctx, genome_len, sample):
     """BASELINE config 2's unit of work: one synthetic sample (5 Mbp at the full size), text resident in HBM,
