@@ -301,63 +301,74 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     if constexpr (Q3_LOOPN > 1 && !INDEL) wn = m.ld(k + 1u);
     if constexpr (Q3_LOOPN > 2 && !INDEL) wn2 = m.ld(k + 2u);
     if constexpr (Q3_LOOPN > 3 && !INDEL) wn3 = m.ld(k + 3u);
-    for (;;) {
-        low = Q3_LOW(w);                                   // bit 7 <-> byte < 0x21 (or >= 0x80): the column ends here
-        if (INDEL) {
-            const uint32_t first = low & (0u - low);
-            const uint32_t valid = low ? (first - 1u) & H : H;                                 // the column's bytes of this word
-            const uint32_t car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & valid;
-            const uint32_t part = funnel_l8(prevcar, car);
-            const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);
-            const uint32_t sign = ~(y3 | part) & valid;                                          // ) + - / that is no "^x" quality
-            if (sign) {
-                const uint32_t fs = sign & (0u - sign);
-                const uint32_t sb = (uint32_t)ctz32(fs) >> 3;                                    // byte of the sign in the word
-                const uint32_t ch = (w >> (8u * sb)) & 0xffu;
-                if (ch != '+' && ch != '-') return ST_DETAIL;
-                const uint32_t v2 = (fs - 1u) & H;                                               // the bytes in front of the sign
-                const uint32_t car2 = car & v2, part2 = part & v2;
-                const uint32_t dol2 = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & v2;
-                const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);
-                const uint32_t dck2 = ~(y2 | part) & v2;
-                const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);
-                an1 |= ~(yr | part) & v2;
-                an2 |= car2 & part2;
-                a_rem = flag_sum(car2 | part2 | dol2, a_rem);
-                a_dc = flag_sum(dck2, a_dc);
-                a_dot = flag_weigh(w, dck2, a_dot);
-                uint32_t t = 4u * k + sb + 1u, n = 0, nd = 0;                                    // the token: 1..3 digits, n symbols
-                while (nd < 3u && (uint32_t)m.byte(t) - '0' < 10u) { n = n * 10u + ((uint32_t)m.byte(t) - '0'); t++; nd++; }
-                if (nd == 0u || (uint32_t)m.byte(t) - '0' < 10u || t + n > limit) return ST_DETAIL;   // a bare sign, a long number
-                for (uint32_t x = 0; x < n; x++) {
-                    const uint32_t c2 = m.byte(t + x);
-                    if ((c2 | 0x20u) - 'a' >= 26u && c2 != '*') return ST_DETAIL;
-                }
-                a_rem += 128u * (1u + nd + n);
-                const uint32_t wpos = t + n;                                                      // go on behind the token
-                k = wpos >> 2;
-                w = m.ld(k);
-                const uint32_t mk = 0xffffffffu << ((wpos & 3u) * 8u);
-                w = (w & mk) | (0x30303030u & ~mk);
-                prevcar = 0;
-                continue;
+    if constexpr (INDEL) {
+        // The second look.  Round by round: all lanes walk their words up to the next sign or the separator (inner loop),
+        // meet again, and the lanes that stopped at a sign skip their token TOGETHER -- one pass of the token code per
+        // round and warp, not one per lane (a line carries one token as a rule, at a different word in every lane).
+        for (;;) {
+            uint32_t sign, car, part;
+            for (;;) {
+                low = Q3_LOW(w);                           // bit 7 <-> byte < 0x21 (or >= 0x80): the column ends here
+                const uint32_t first = low & (0u - low);
+                const uint32_t valid = low ? (first - 1u) & H : H;                             // the column's bytes of this word
+                car = Q3_ADD(0x22222222u, w) & Q3_NADD(0x21212121u, w) & valid;
+                part = funnel_l8(prevcar, car);
+                const uint32_t y3 = Q3_ADD(0x7f7f7f7fu, (w & MF9) ^ 0x29292929u);
+                sign = ~(y3 | part) & valid;                                                   // ) + - / that is no "^x" quality
+                if ((sign | low) != 0u) break;
+                Q3_BASES_WORD(w);
+                w = m.ld(++k);
             }
+            if (sign == 0u) break;                         // the separator's word: the common tail takes it
+            const uint32_t fs = sign & (0u - sign);
+            const uint32_t sb = (uint32_t)ctz32(fs) >> 3;                                      // byte of the sign in the word
+            const uint32_t ch = (w >> (8u * sb)) & 0xffu;
+            if (ch != '+' && ch != '-') return ST_DETAIL;
+            const uint32_t v2 = (fs - 1u) & H;                                                 // the bytes in front of the sign
+            const uint32_t car2 = car & v2, part2 = part & v2;
+            const uint32_t dol2 = Q3_ADD(0x5c5c5c5cu, w) & Q3_NADD(0x5b5b5b5bu, w) & v2;
+            const uint32_t y2 = Q3_ADD(0x7f7f7f7fu, (w & MFD) ^ 0x2c2c2c2cu);
+            const uint32_t dck2 = ~(y2 | part) & v2;
+            const uint32_t yr = Q3_ADD(0x7f7f7f7fu, (w | 0x20202020u) ^ refb);
+            an1 |= ~(yr | part) & v2;
+            an2 |= car2 & part2;
+            a_rem = flag_sum(car2 | part2 | dol2, a_rem);
+            a_dc = flag_sum(dck2, a_dc);
+            a_dot = flag_weigh(w, dck2, a_dot);
+            uint32_t t = 4u * k + sb + 1u, n = 0, nd = 0;                                      // the token: 1..3 digits, n symbols
+            while (nd < 3u && (uint32_t)m.byte(t) - '0' < 10u) { n = n * 10u + ((uint32_t)m.byte(t) - '0'); t++; nd++; }
+            if (nd == 0u || (uint32_t)m.byte(t) - '0' < 10u || t + n > limit) return ST_DETAIL;   // a bare sign, a long number
+            for (uint32_t x = 0; x < n; x++) {
+                const uint32_t c2 = m.byte(t + x);
+                if ((c2 | 0x20u) - 'a' >= 26u && c2 != '*') return ST_DETAIL;
+            }
+            a_rem += 128u * (1u + nd + n);
+            const uint32_t wpos = t + n;                                                        // go on behind the token
+            k = wpos >> 2;
+            w = m.ld(k);
+            const uint32_t mk = 0xffffffffu << ((wpos & 3u) * 8u);
+            w = (w & mk) | (0x30303030u & ~mk);
+            prevcar = 0;
         }
-        if (low) break;
-        if constexpr (Q3_LOOPN > 1 && !INDEL) {            // several words a trip, each left as soon as it holds the separator:
-            Q3_BASES_WORD(w);                              // the later words' loads have whole words' work to arrive
+    } else {
+        for (;;) {
+            low = Q3_LOW(w);                               // bit 7 <-> byte < 0x21 (or >= 0x80): the column ends here
+            if (low) break;
+            if constexpr (Q3_LOOPN > 1) {                  // several words a trip, each left as soon as it holds the separator:
+                Q3_BASES_WORD(w);                          // the later words' loads have whole words' work to arrive
 #define Q3_NEXT_WORD(x) w = (x); ++k; low = Q3_LOW(w); if (low) break; Q3_BASES_WORD(w)
-            Q3_NEXT_WORD(wn);
-            if constexpr (Q3_LOOPN > 2) { Q3_NEXT_WORD(wn2); }
-            if constexpr (Q3_LOOPN > 3) { Q3_NEXT_WORD(wn3); }
+                Q3_NEXT_WORD(wn);
+                if constexpr (Q3_LOOPN > 2) { Q3_NEXT_WORD(wn2); }
+                if constexpr (Q3_LOOPN > 3) { Q3_NEXT_WORD(wn3); }
 #undef Q3_NEXT_WORD
-            w = m.ld(++k);
-            wn = m.ld(k + 1u);
-            if constexpr (Q3_LOOPN > 2) wn2 = m.ld(k + 2u);
-            if constexpr (Q3_LOOPN > 3) wn3 = m.ld(k + 3u);
-        } else {
-            Q3_BASES_WORD(w);
-            w = m.ld(++k);
+                w = m.ld(++k);
+                wn = m.ld(k + 1u);
+                if constexpr (Q3_LOOPN > 2) wn2 = m.ld(k + 2u);
+                if constexpr (Q3_LOOPN > 3) wn3 = m.ld(k + 3u);
+            } else {
+                Q3_BASES_WORD(w);
+                w = m.ld(++k);
+            }
         }
     }
     uint32_t q0;
