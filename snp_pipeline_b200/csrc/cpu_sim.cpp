@@ -102,6 +102,15 @@ int cpusim_pileup(const uint8_t *text, size_t nbytes, const char *contig_names, 
                         if (st == ST_TALLY) {                            // well-formed, only the call is left: queued with its end known
                             if (q3.end != e) { counters[3] = s; counters[4] = 94; break; }   // harness self-check: that end
                             st = ST_DETAIL;
+                        } else if (st == ST_ZERO) {                      // depth 0: queued; the follow-up kernel's first tier calls it
+                            uint32_t odd2 = 0;                           // ('-', RawDpth) unless the pileup kernel saw something odd
+                            if (q3_find_nl(m, q3.end, 1u, &odd2) != e) { counters[3] = s; counters[4] = 90; break; }   // harness self-check
+                            bool odd_q = false;
+                            for (size_t x = q3.end; x < e; x++) odd_q |= (buf[x] >= 0x0b && buf[x] <= 0x0d) || buf[x] >= 0x80;
+                            if (odd_q && !odd2) { counters[3] = s; counters[4] = 89; break; }
+                            if (odd2) st = ST_DETAIL;
+                            else if (q3_rest<true>(m, q3.after, (uint32_t)e, *p, 1u, &q3) != ST_ZERO) { counters[3] = s; counters[4] = 88; break; }
+                            else { st = ST_OK; q3.end = (uint32_t)e; q3.base = (uint8_t)'-'; q3.fail = FAIL_RAWDPTH; }
                         } else if (st == ST_SIGN) {                      // the pileup kernel looks for the line end from the quality column on
                             uint32_t odd2 = 0;
                             if (q3_find_nl(m, q3.end, 1u, &odd2) != e) { counters[3] = s; counters[4] = 93; break; }   // harness self-check

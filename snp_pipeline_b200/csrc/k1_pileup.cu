@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM) k1_pileup_kernel(c
                         next = q.end + 1u;
                     } else {
                         uint32_t odd = 0;
-                        const uint32_t e = q3_find_nl(m, st == ST_SIGN ? q.end : s, one, &odd);   // (ST_SIGN: columns 1-5 are clean)
+                        const uint32_t e = q3_find_nl(m, st == ST_SIGN || st == ST_ZERO ? q.end : s, one, &odd);   // (columns 1-5 / 1-4 are clean)
                         push = true;
                         push_len = e < wlen || eof ? e - s : 0u;
                         push_flag = odd ? 1u : 0u;
@@ -393,7 +393,11 @@ __device__ __forceinline__ bool k1_rest_quick(const K1Batch &g, const K1Samp &S,
     const uint32_t bb = q.pos & 31u;
     if ((int32_t)q.pos <= cc.max_pos) sw = load_site_word(g.sites.words + cc.word_base + (q.pos >> 5));
     if (!all && !((sw.any >> bb) & 1u)) return false;
-    if (q3_rest<true>(m, q.after, limit, g.p, one, &q) != ST_OK || q.end != limit) return false;
+    const int st = q3_rest<true>(m, q.after, limit, g.p, one, &q);
+    if (st == ST_ZERO) {                                      // depth 0 (pileup.py:226-234): ('-', RawDpth) whatever follows -- the pileup
+        q.base = (uint8_t)'-';                                // kernel saw no CR / VT / FF / byte >= 0x80 in the line (else K1_Q_GENERAL)
+        q.fail = FAIL_RAWDPTH;
+    } else if (st != ST_OK || q.end != limit) return false;
     unsigned fail = q.fail;
     if ((sw.exc >> bb) & 1u) fail |= FAIL_REGION;
     const unsigned cell = fail ? (unsigned)'-' : q.base;

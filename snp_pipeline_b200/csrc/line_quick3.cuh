@@ -29,6 +29,8 @@ namespace snpgpu {
 enum : int { ST_DETAIL = 67 };         // "not for this tier": the line goes to the follow-up kernel, no side effects
 enum : int { ST_TALLY = 68 };          // declined like ST_DETAIL, but the line is well-formed and out->end is its '\n':
                                        // only the call needs the per-letter tallies of the second tier
+enum : int { ST_ZERO = 70 };           // raw depth 0 with columns 1-4 well-formed: out->end is the byte behind the depth column's tab;
+                                       // the call is ('-', RawDpth) once the rest of the line shows no CR / VT / FF / byte >= 0x80
 enum : int { ST_SIGN = 69 };           // declined like ST_DETAIL by the first look (INDEL = false) over a '+' / '-' / ')' / '/' in
                                        // the bases column -- an indel token, as a rule: columns 1-5 hold no separator but
                                        // their tabs and no byte >= 0x80, out->end is the first byte of the quality column
@@ -282,9 +284,12 @@ SNP_HD int q3_rest(const M &m, uint32_t i, uint32_t limit, const CallParams &p, 
     const uint32_t n2 = nd ? (uint32_t)ctz32(nd) >> 3 : 4u;
     bad |= n2 == 0u || n2 == 4u;                           // (four digits or more: next tier)
     bad |= ((d >> (8u * (n2 & 3u))) & 0xffu) != '\t';
-    bad |= (y & ((1u << (8u * (n2 & 3u))) - 1u)) == 0u;    // depth 0: pileup.py:226-234, left to the detailed parser
     if (bad) return ST_DETAIL;
     const uint32_t b0 = i + 3u + n2;                       // first byte of the bases column
+    if ((y & ((1u << (8u * (n2 & 3u))) - 1u)) == 0u) {     // depth 0 (pileup.py:226-234): whatever follows is ignored
+        out->end = b0;
+        return ST_ZERO;
+    }
     // ---- column 5: bases, aligned words -----------------------------------------------------------------
     const uint32_t refb = (ref | 0x20u) * 0x01010101u;
     const uint32_t MFD = one * 0xfdfdfdfdu, MF9 = one * 0xf9f9f9f9u;   // (in registers: one LOP3 per masked compare)

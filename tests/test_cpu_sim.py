@@ -335,3 +335,31 @@ def test_odd_bytes_in_columns(sim, seed):
         lines[k] = b"\t".join(f)
         for all_pos in (True, False):
             _compare(sim, b"".join(lines), [(linegen.CHROM, 1 + k)], [], PARAM_SETS[sub % len(PARAM_SETS)], all_pos)
+
+
+ZERO_TAILS = ["*\t*", "\t", "", "*", "*\t*\textra\tcolumns", "* *", "..,\tII", "*\t*\r", "*\r*", "*\t\x0b", "\x80\t*", "*\t\xa1",
+              "+2AC\t!", "\x1c\x1d", " ", "*\t*\t", "^", "\t\t\t"]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_zero_depth_lines(sim, seed):
+    """Raw depth 0 (pileup.py:226-234): the call is ('-', RawDpth) whatever follows the depth column; the first tier takes
+    such lines itself unless the rest holds a CR / VT / FF or a byte >= 0x80 (lone CR ends a line, high bytes are out of
+    the domain) -- every shape against the oracle, between ordinary lines."""
+    rng = random.Random(seed)
+    lines = []
+    for k in range(160):
+        if k % 2:
+            lines.append(linegen.realistic_line(rng, 1 + k).encode("latin-1"))
+            continue
+        depth = rng.choice(["0", "0", "00", "000", "0000"])
+        ref = rng.choice("ACGTNacgtnRr*")
+        tail = rng.choice(ZERO_TAILS)
+        sep = rng.choice(["\t", "\t", "\t", " ", ""])
+        nl = rng.choice(["\n", "\n", "\r\n"])
+        lines.append(("%s\t%d\t%s\t%s%s%s%s" % (linegen.CHROM, 1 + k, ref, depth, sep, tail, nl)).encode("latin-1"))
+    snps = [(linegen.CHROM, 1 + k) for k in range(0, 160, 3)]
+    for all_pos in (True, False):
+        for k in range(0, 160, 2):                                 # one odd line at a time between ordinary ones (errors stop a run)
+            text = b"".join(lines[max(0, k - 1):k + 2])
+            _compare(sim, text, snps, [], PARAM_SETS[k % len(PARAM_SETS)], all_pos)

@@ -222,6 +222,40 @@ def test_nasty_text(ctx, seed):
             _compare(ctx, text, snps, excl, ps, all_pos)
 
 
+@pytest.mark.parametrize("seed", range(2))
+def test_zero_depth_and_odd_bytes(ctx, seed):
+    """Lines of raw depth 0 in every shape (the pileup kernel's first tier calls them itself unless something odd follows
+    the depth column) and lines with one byte >= 0x80 / control byte in some column, each between ordinary lines."""
+    import test_cpu_sim as tcs
+    rng = random.Random(40 + seed)
+    lines = [linegen.realistic_line(rng, 1 + k, indel_rate=0.03).encode("latin-1") for k in range(400)]
+    snps = [(linegen.CHROM, 1 + k) for k in range(0, 400, 3)]
+    clean = []
+    for k in range(0, 400, 4):
+        if k % 8:
+            tail = rng.choice(tcs.ZERO_TAILS)
+            ln = ("%s\t%d\t%s\t%s%s%s\n" % (linegen.CHROM, 1 + k, rng.choice("ACGTNacgtn"), rng.choice(["0", "00", "000"]),
+                                           rng.choice(["\t", "\t", " "]), tail)).encode("latin-1")
+        else:
+            f = lines[k].split(b"\t")
+            col = rng.choice([4, 4, 5, 1, 0])
+            b = bytearray(f[col])
+            b[rng.randrange(len(b))] = rng.choice([0x80, 0xa0, 0xa1, 0xff, 0x7f, 0x20, 0x1f, 0x0b, 0x00])
+            f[col] = bytes(b)
+            ln = b"\t".join(f)
+        try:                                                   # lines the reference takes stay in the long text as well
+            orc.pileup_consensus(ln, [], [], orc.make_params(), parse_all=True, want_lines=True)
+            lines[k] = ln
+            clean.append(k)
+        except orc.OracleError:
+            pass
+        for all_pos in (True, False):                          # ... and every line alone between two ordinary ones
+            _compare(ctx, lines[k - 1] + ln + lines[k + 1] if k else ln + lines[1], snps, [], PARAM_SETS[k % len(PARAM_SETS)], all_pos)
+    assert len(clean) > 20
+    for all_pos in (True, False):
+        _compare(ctx, b"".join(lines), snps, [], PARAM_SETS[1], all_pos)
+
+
 def test_reference_file_vectors(ctx, ref_files):
     """Vectors produced by the reference's own `call_consensus` (tests/golden/make_golden.py)."""
     from snp_pipeline_b200 import _lib
