@@ -142,6 +142,11 @@ class Workload(object):
         self.lines_dev = torch.empty((self.n, args.genome_len + 64), dtype=torch.int16, device="cuda")
         self.stats_dev = torch.zeros((self.n, 6), dtype=torch.int64, device="cuda")
         self.params = _lib.make_params(min_cons_depth=3)
+        # the batch's descriptors (snpgpu_pileup_sample), built once: a step only fills in where its matrix rows lie
+        self.batch_arr = (_lib.PileupSample * self.n)()
+        for i in range(self.n):
+            self.batch_arr[i] = _lib.PileupSample(self.texts[i].data_ptr(), int(self.nbytes[i]), None, self.lines_dev[i].data_ptr(),
+                                                  args.genome_len + 64, self.stats_dev[i].data_ptr())
 
     def spec(self, i):
         a = self.args
@@ -178,9 +183,10 @@ def device_step(w, dist, world):
     sites = w.lib.Sites.from_keys_dev(ctx, [CONTIG], [w.args.genome_len], local.data_ptr(), n_uniq)
     matrix = torch.empty((w.n, (max(n_uniq, 1) + 63) // 64 * 64), dtype=torch.uint8, device="cuda")    # 16-byte aligned rows
     # one launch sequence per <= 64 samples (snpgpu_pileup_consensus_batch_dev); every sample has its own per-line results
-    ctx.pileup_consensus_batch_dev([(w.texts[i].data_ptr(), w.nbytes[i], matrix[i].data_ptr(), w.lines_dev[i].data_ptr(),
-                                     w.args.genome_len + 64, w.stats_dev[i].data_ptr()) for i in range(w.n)],
-                                   sites, w.params, w.lib.MODE_ALL)
+    row0, pitch = matrix.data_ptr(), matrix.shape[1]
+    for i in range(w.n):
+        w.batch_arr[i].row_out_dev = row0 + i * pitch
+    ctx.pileup_consensus_batch_dev(w.batch_arr, sites, w.params, w.lib.MODE_ALL)
     full = sharding.allgather_rows(matrix, dist, world)
     lo = w.rank * w.n
     d = torch.empty((w.n, full.shape[0]), dtype=torch.int32, device="cuda")

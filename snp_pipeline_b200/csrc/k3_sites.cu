@@ -4,8 +4,8 @@
 // (utils.write_list_of_snps utils.py:1056-1070 -> utils.read_snp_position_list utils.py:1073-1088) and every
 // call_consensus process builds its set of positions from that file (call_consensus.py:133, :147-151).  When both
 // steps run in one process on one GPU the list never has to leave HBM: the sorted unique keys K2 wrote are turned
-// into the table K1 probes (sites.cuh) by four small kernels: set the bits, prefix sum of the words' popcounts (one block:
-// 156 k words for 5 Mbp), pack the per-word records, resolve every snplist entry to its unique-site index.
+// into the table K1 probes (sites.cuh) by a few small kernels: set the bits, prefix sum of the words' popcounts (block sums,
+// their offsets, per-block scan: 156 k words for 5 Mbp), pack the per-word records, resolve every snplist entry to its unique-site index.
 #include "internal.h"
 
 namespace snpgpu {
@@ -43,23 +43,66 @@ __global__ void k3_unique_kernel(const unsigned long long *keys, size_t n, int n
     snp_unique[i] = u;
 }
 
-// rank[w] = number of set bits in bits[0 .. w): exclusive prefix over the words' popcounts, one block
-constexpr int K3_SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(K3_SCAN_THREADS) k3_rank_kernel(const uint32_t *bits, size_t n_words, uint32_t *rank) {
-    __shared__ uint32_t part[K3_SCAN_THREADS];
-    const size_t per = (n_words + K3_SCAN_THREADS - 1) / K3_SCAN_THREADS;
-    const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < n_words ? lo + per : n_words;
-    uint32_t s = 0;
-    for (size_t i = lo; i < hi; i++) s += (uint32_t)__popc(bits[i]);
-    part[threadIdx.x] = s;
+// rank[w] = number of set bits in bits[0 .. w): exclusive prefix over the words' popcounts.  Three small kernels: every
+// block sums the popcounts of its K3_CHUNK words; one block turns the sums into exclusive offsets; every block scans its
+// own words from its offset (a single block over the 156 k words of a 5 Mbp contig took 0.17 ms per site table).
+constexpr int K3_SCAN_THREADS = 256;
+constexpr int K3_PER_THREAD = 8;
+constexpr int K3_CHUNK = K3_SCAN_THREADS * K3_PER_THREAD;
+// exclusive prefix of v over the block's threads (in thread order); *total = the block's sum
+__device__ __forceinline__ uint32_t k3_block_exclusive(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int t = 0; t < K3_SCAN_THREADS; t++) { const uint32_t v = part[t]; part[t] = run; run += v; }
+    uint32_t before = 0, all = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+        const uint32_t s = warp_sums[w];
+        if (w < warp) before += s;
+        all += s;
     }
     __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (size_t i = lo; i < hi; i++) { rank[i] = run; run += (uint32_t)__popc(bits[i]); }
+    *total = all;
+    return before + incl - v;
+}
+__global__ void __launch_bounds__(K3_SCAN_THREADS) k3_rank_sum_kernel(const uint32_t *bits, size_t n_words, uint32_t *part) {
+    __shared__ uint32_t ws[K3_SCAN_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * K3_CHUNK + (size_t)threadIdx.x * K3_PER_THREAD;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < K3_PER_THREAD; j++) if (base + j < n_words) s += (uint32_t)__popc(bits[base + j]);
+    uint32_t total;
+    k3_block_exclusive(s, ws, &total);
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k3_rank_offsets_kernel(uint32_t *part, size_t n_blocks) {    // one block, in place
+    __shared__ uint32_t ws[32];
+    uint32_t carry = 0;
+    for (size_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const size_t i = b0 + threadIdx.x;
+        const uint32_t v = i < n_blocks ? part[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = k3_block_exclusive(v, ws, &total);
+        if (i < n_blocks) part[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(K3_SCAN_THREADS) k3_rank_kernel(const uint32_t *bits, size_t n_words, const uint32_t *part,
+                                                                  uint32_t *rank) {
+    __shared__ uint32_t ws[K3_SCAN_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * K3_CHUNK + (size_t)threadIdx.x * K3_PER_THREAD;
+    uint32_t c[K3_PER_THREAD], s = 0;
+#pragma unroll
+    for (int j = 0; j < K3_PER_THREAD; j++) { c[j] = base + j < n_words ? (uint32_t)__popc(bits[base + j]) : 0u; s += c[j]; }
+    uint32_t total;
+    uint32_t run = part[blockIdx.x] + k3_block_exclusive(s, ws, &total);
+#pragma unroll
+    for (int j = 0; j < K3_PER_THREAD; j++) { if (base + j < n_words) rank[base + j] = run; run += c[j]; }
 }
 
 // bits + rank -> the packed words of the first-tier parser (every site is a snplist entry, none is excluded)
@@ -68,7 +111,7 @@ __global__ void k3_pack_words_kernel(const uint32_t *bits, const uint32_t *rank,
     if (w < n_words) words[w] = SiteWord{bits[w], bits[w], 0u, rank[w]};
 }
 
-size_t k3_scan_bytes(size_t) { return 0; }                   // (the rank kernel needs no workspace)
+size_t k3_scan_bytes(size_t n_words) { return ((n_words + K3_CHUNK - 1) / K3_CHUNK + 1) * sizeof(uint32_t); }   // the blocks' popcount sums
 
 // bits / rank: n_words words each, bits zeroed here; returns the number of kernels launched, or < 0
 int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int n_contigs, const int64_t *bit_base,
@@ -80,14 +123,20 @@ int k3_launch(cudaStream_t stream, const unsigned long long *keys, size_t n, int
         k3_set_bits_kernel<<<(unsigned)((n + 256) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, flags);
         launches++;
     }
-    (void)tmp; (void)tmp_bytes;
-    k3_rank_kernel<<<1, K3_SCAN_THREADS, 0, stream>>>(bits, n_words, rank);
+    const size_t n_blocks = (n_words + K3_CHUNK - 1) / K3_CHUNK;
+    if (tmp_bytes < k3_scan_bytes(n_words)) return -1;
+    uint32_t *part = reinterpret_cast<uint32_t *>(tmp);
+    if (n_blocks) {
+        k3_rank_sum_kernel<<<(unsigned)n_blocks, K3_SCAN_THREADS, 0, stream>>>(bits, n_words, part);
+        k3_rank_offsets_kernel<<<1, 1024, 0, stream>>>(part, n_blocks);
+        k3_rank_kernel<<<(unsigned)n_blocks, K3_SCAN_THREADS, 0, stream>>>(bits, n_words, part, rank);
+    }
     k3_pack_words_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(bits, rank, n_words, words);
     if (n) {
         k3_unique_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, n_contigs, bit_base, max_pos, bits, rank, snp_unique);
         launches++;
     }
-    return launches + 2;
+    return launches + (n_blocks ? 4 : 1);
 }
 
 // ---- reference bases at the snplist positions (utils.write_reference_snp_file, utils.py:1091-1110): out[k] =
