@@ -40,7 +40,10 @@ constexpr int K1_TILE        = 32 * K1_LANE_BYTES;   // bytes of text whose line
 constexpr int K1_LOOK        = K1_CFG_LOOK;          // extra bytes staged so that the last owned line is complete
 constexpr int K1_WIN         = K1_TILE + K1_LOOK;
 constexpr int K1_PAD         = 32;                   // '\n' sentinels after the staged bytes (word over-reads land here)
-constexpr int K1_LCAP        = 8;                    // per-line results a lane keeps in the staging array per tile (more -> overflow list)
+#ifndef K1_CFG_LCAP
+#define K1_CFG_LCAP 8
+#endif
+constexpr int K1_LCAP        = K1_CFG_LCAP;          // per-line results a lane keeps in the staging array per tile (more -> overflow list)
 constexpr int K1_ORDER_TILES = 512;                  // tiles per group of the ordering pass (k1_tile_prefix_kernel)
 constexpr int K1_NAMEW       = 16;                   // words of the expected contig's name a warp keeps in shared memory
 #ifndef K1_CFG_BATCH
