@@ -317,9 +317,20 @@ def cpu_baseline(w, matrix_host, n_samples):
 
 
 def reference_python_leg(w, n_lines=150_000):
-    """The reference's OWN Python (staged under oracle/_ref by oracle/stage_ref.py, unmodified) on the first n_lines of
-    one synthetic sample: pileup.Reader over every line + ConsensusCaller.call_consensus per record, one core -- the loop
-    of call_consensus.py:161-176 without the file writing.  None when the modules are not staged."""
+    """cpu_baseline.reference_python of the GPU arm: reference_python_legs() on the rank's first synthetic sample."""
+    text = w.texts[0][:w.nbytes[0]].cpu().numpy().tobytes()
+    return reference_python_legs(text, w.site_pos[0], n_lines)
+
+
+def reference_python_legs(text, own_sites, n_lines=150_000):
+    """The reference's OWN Python (staged under oracle/_ref by oracle/stage_ref.py, unmodified), one core, on the GPU box's
+    host (SURVEY.md section 8d "CPU baseline timing"):
+      (ii)  pileup.Reader over every one of the first n_lines lines of one synthetic sample + ConsensusCaller.call_consensus
+            per record -- the loop of call_consensus.py:161-176 without the file writing (--vcfAllPos);
+      (iii) the same file in the default filter mode (Reader with the sample's own sites as the position set);
+      (iv)  utils.calculate_sequence_distance over all pairs of 40 x 10 000-site rows (distance.py:93-96);
+      (i)   the reference's four subcommands on the bundled lambda data (tests/golden/lambda.tar.xz), wall time per stage.
+    None when the modules are not staged."""
     import tempfile
     from oracle import stage_ref
     root = stage_ref.staged_root()
@@ -332,7 +343,6 @@ def reference_python_leg(w, n_lines=150_000):
         pileup = ref_harness.ref("pileup")
     except Exception as e:  # noqa: BLE001
         return {"unavailable": repr(e)[:200]}
-    text = w.texts[0][:w.nbytes[0]].cpu().numpy().tobytes()
     end, k = 0, 0
     while k < n_lines:
         nxt = text.find(b"\n", end)
@@ -342,6 +352,7 @@ def reference_python_leg(w, n_lines=150_000):
     with tempfile.NamedTemporaryFile("wb", suffix=".pileup", delete=False) as f:
         f.write(text[:end])
         path = f.name
+    out = {"cores": 1}
     try:
         caller = pileup.ConsensusCaller(0.6, 3, 0, 0.0)
         t0 = time.perf_counter()
@@ -350,11 +361,85 @@ def reference_python_leg(w, n_lines=150_000):
             caller.call_consensus(record)
             n += 1
         dt = time.perf_counter() - t0
+        out.update({"positions_per_s_per_core": n / dt, "lines_timed": n, "seconds": dt,
+                    "what": "snppipeline/pileup.py (unmodified, staged by oracle/stage_ref.py): Reader(all positions) + "
+                            "ConsensusCaller.call_consensus per record"})
+        wanted = set((CONTIG, int(p)) for p in own_sites)
+        t0 = time.perf_counter()
+        n_f = hits = 0
+        for record in pileup.Reader(path, 0, wanted):
+            caller.call_consensus(record)
+            hits += 1
+        n_f = k
+        dt = time.perf_counter() - t0
+        out["filter_mode"] = {"positions_per_s_per_core": n_f / dt, "lines_timed": n_f, "lines_at_sites": hits, "seconds": dt,
+                              "what": "the default mode of run.py:709: Reader(position set = the sample's own sites), "
+                                      "records only at the sites"}
     finally:
         os.unlink(path)
-    return {"positions_per_s_per_core": n / dt, "cores": 1, "lines_timed": n, "seconds": dt,
-            "what": "snppipeline/pileup.py (unmodified, staged by oracle/stage_ref.py): Reader(all positions) + "
-                    "ConsensusCaller.call_consensus per record"}
+    try:                                                        # (iv) the distance loop of the reference
+        utils = ref_harness.ref("utils")
+        rng = np.random.default_rng(5)
+        rows = ["".join(r) for r in np.array(list("ACGTN-acgt"))[rng.integers(0, 10, size=(40, 10_000))]]
+        t0 = time.perf_counter()
+        for i in range(len(rows)):
+            for j in range(i + 1, len(rows)):
+                utils.calculate_sequence_distance(rows[i], rows[j])
+        dt = time.perf_counter() - t0
+        pairs = len(rows) * (len(rows) - 1) // 2
+        out["distance"] = {"pair_sites_per_s_per_core": pairs * 10_000 / dt, "pairs": pairs, "sites": 10_000, "seconds": dt,
+                           "what": "utils.calculate_sequence_distance (utils.py:1135-1165) over all pairs of 40 rows"}
+    except Exception as e:  # noqa: BLE001
+        out["distance"] = {"unavailable": repr(e)[:200]}
+    try:
+        out["c1_lambda"] = reference_c1_stages(ref_harness)
+    except BaseException as e:  # noqa: BLE001  (the reference's error paths end in sys.exit)
+        out["c1_lambda"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
+def reference_c1_stages(ref_harness):
+    """BASELINE configs[0]: the reference's own merge_sites -> call_consensus x 4 -> snp_matrix -> distance on the bundled
+    lambda-virus samples (4 x 48 502 positions, 166 sites), in-process through its command-line parser, wall seconds per
+    stage; the consensus files are compared with the bundled expected ones."""
+    import contextlib
+    import io
+    import tarfile
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        with tarfile.open(os.path.join(ROOT, "tests", "golden", "lambda.tar.xz")) as tar:
+            tar.extractall(tmp, filter="data")
+        base = os.path.join(tmp, "lambda")
+        dirs = sorted(os.path.join(base, "samples", d) for d in os.listdir(os.path.join(base, "samples")))
+        work = os.path.join(tmp, "work")
+        os.makedirs(work)
+        sdf = os.path.join(work, "sampleDirectories.txt")
+        with open(sdf, "w") as f:
+            f.write("".join(d + "\n" for d in dirs))
+        expected = {d: open(os.path.join(d, "consensus.fasta")).read() for d in dirs}
+        for d in dirs:
+            os.rename(os.path.join(d, "consensus.fasta"), os.path.join(d, "consensus.expected"))
+        snplist, snpma = os.path.join(work, "snplist.txt"), os.path.join(work, "snpma.fasta")
+        stages = {}
+        sink = io.StringIO()
+
+        def run(stage, line):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+                ref_harness.run_command(line)
+            stages[stage] = stages.get(stage, 0.0) + time.perf_counter() - t0
+
+        run("merge_sites", "merge_sites -f -n var.flt.vcf -o %s %s %s" % (snplist, sdf, os.path.join(work, "filtered.txt")))
+        for d in dirs:
+            run("call_consensus", "call_consensus -f -l %s -o %s %s" % (snplist, os.path.join(d, "consensus.fasta"),
+                                                                     os.path.join(d, "reads.all.pileup")))
+        run("snp_matrix", "snp_matrix -f -c consensus.fasta -o %s %s" % (snpma, sdf))
+        run("distance", "distance -f -p %s -m %s %s" % (os.path.join(work, "pairwise.tsv"), os.path.join(work, "matrix.tsv"), snpma))
+        same = all(open(os.path.join(d, "consensus.fasta")).read() == expected[d] for d in dirs)
+        return {"stage_seconds": stages, "samples": len(dirs), "positions_per_sample": 48502,
+                "consensus_identical_to_bundled": same,
+                "what": "the reference's own subcommands (run_command_from_line, default parameters, no consensus.vcf) on "
+                        "tests/golden/lambda.tar.xz, one process, one core"}
 
 
 def run_reference(args, rank):
@@ -393,6 +478,12 @@ def run_reference(args, rank):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     value = n_ref * args.genome_len / dt
+    ref_py = None
+    if not args.no_cpu:
+        try:                                                 # the reference's own Python beside its C restatement (one core)
+            ref_py = reference_python_legs(texts[0].tobytes(), site_pos[0])
+        except Exception as e:  # noqa: BLE001
+            ref_py = {"unavailable": repr(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "positions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -400,7 +491,8 @@ def run_reference(args, rank):
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "positions/s", "cores": min(cores, n_ref), "kind": "port",
                          "sample": "%d of %d samples per step, one thread each (oracle/snp_oracle.c, all-positions "
-                                   "mode) + K2 and K4 on those samples" % (n_ref, args.samples)},
+                                   "mode) + K2 and K4 on those samples" % (n_ref, args.samples),
+                         "reference_python": ref_py},
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -27,3 +27,30 @@ def test_host_text_is_reproducible_and_well_formed():
     ref = np.array([lines[int(p) - 1].split(b"\t")[2][0] for p in own], dtype=np.uint8)
     called = np.frombuffer(row, dtype=np.uint8)
     assert np.mean((called != ref) & (called != ord("-"))) > 0.8
+
+
+def test_bench_reference_arm_runs_without_the_gpu_library():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line with the contract's
+    keys, inputs from the host generator, and neither torch nor the GPU library imported by that process."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json, io, contextlib; sys.argv = ['bench.py', '--impl', 'reference', '--samples', '2', '--genome-len', '60000', "
+            "'--steps', '1', '--warmup', '1']; import bench; bench.main(); "
+            "print(json.dumps({'torch': 'torch' in sys.modules, 'lib': 'snp_pipeline_b200._lib' in sys.modules}))")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    line, loaded = json.loads(lines[-2]), json.loads(lines[-1])
+    assert loaded == {"torch": False, "lib": False}
+    assert line["impl"] == "reference" and line["unit"] == "positions/s" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["e2e"] == {"value": line["value"], "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"]
+    rp = cb["reference_python"]
+    if rp is not None and "unavailable" not in rp:             # (only where oracle/stage_ref.py staged the reference's modules)
+        assert rp["positions_per_s_per_core"] > 0 and rp["filter_mode"]["positions_per_s_per_core"] > 0
+        assert rp["distance"]["pair_sites_per_s_per_core"] > 0
+        assert rp["c1_lambda"]["consensus_identical_to_bundled"] is True
