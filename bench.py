@@ -960,7 +960,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, d_cpu = cpu_baseline(w, matrix_host, min(args.cpu_samples, w.n))
         assert np.array_equal(d_cpu, d_host), "cpu_baseline: the oracle's distance matrix differs from the GPU's"
-        cpu["reference_python"] = reference_python_leg(w)
+        try:
+            cpu["reference_python"] = reference_python_leg(w)
+        except Exception as e:  # noqa: BLE001  (a reported baseline: its failure must not cost the run its line)
+            cpu["reference_python"] = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         line = {
