@@ -11,11 +11,12 @@
 //     async copy (TMA engine, mbarrier completion); the other resident warps compute while this one waits;
 //   * NO scan pass: lane L owns the lines whose preceding '\n' lies in ITS K1_LANE_BYTES of the tile.  It looks for the
 //     first '\n' of its range (a few words) and then walks its lines one after the other -- a line's end is where the
-//     parse of its quality column ends (line_quick2.cuh), so nothing has to find, order or list line starts beforehand.
+//     parse of its quality column ends (line_quick3.cuh), so nothing has to find, order or list line starts beforehand.
 //     The 32 lanes run their k-th lines in lock step; a tile is sized so that a lane owns just under 4 lines;
-//   * the first tier (line_quick2.cuh) reads the columns as aligned words; a line it declines costs the lane one search
+//   * the first tier (line_quick3.cuh) reads the columns as aligned words; a line it declines costs the lane one search
 //     for its '\n' and goes, by file offset, to a global queue that k1_rest_kernel works through densely afterwards
-//     (line_fast.cuh -> line_general.cuh, one thread per line) -- the hot kernel carries none of that code;
+//     (a second look by the first tier with indel tokens skipped, then line_fast.cuh -> line_general.cuh, one thread per
+//     line) -- the hot kernel carries none of that code;
 //   * results: atomicMax per hit site keeps the LAST line of a position in file order (the dict overwrite of
 //     call_consensus.py:169-176); in all-positions mode the uint16 of a lane's k-th line goes to slot [tile][k][lane] of
 //     the staging array (one coalesced 64-byte store per warp-step), and the slots are put into file order by two small
