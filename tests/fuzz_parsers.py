@@ -3,7 +3,8 @@ against the oracle on indel-corner lines, realistic lines with many indel tokens
 and linegen's nasty lines (IUPAC, '>' / '<', "^x" chains, short quality strings, CRLF, no final newline).
     python tests/fuzz_parsers.py [seconds] [first_seed]
 Last runs of round 1: 600 s, 12 847 texts x 400 lines of the first three kinds and 480 s, 11 858 texts x 300 nasty
-lines: no mismatch."""
+lines: no mismatch.  Round 2, final parsers (byte >= 0x80 ends a column, ST_SIGN / ST_ZERO outcomes, token rounds in the
+second look): 600 s from seed 31337000, 10 937 texts x 400 lines, no mismatch."""
 import ctypes
 import os
 import random
